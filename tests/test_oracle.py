@@ -1,0 +1,184 @@
+"""Pins for the CPU oracle (oracle/rem2d_oracle.c).
+
+* control_pin: controller + P-control + wall of death against the reference's own step() run on a
+  frozen fake Box2D world (tests/golden/control_pin.json)                               (a9, a10, a12)
+* analytic known answers for the Box2D-2.3 restatement (pin P3): free fall, resting
+  contact depth and manifold, interior-vertex circle contacts, motor torque saturation, limit snap,
+  sleeping, wall-of-death lifetime.
+The oracle is parity-UNPINNED against real pybox2d (not installable); these tests pin what can be.
+"""
+import json
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+from gym_rem2d_b200 import Individual, constants as K, terrain
+from gym_rem2d_b200.encodings.direct import DirectEncoding
+from gym_rem2d_b200.flatten import CreatureTable, flatten_tree, pack, flatten_population
+from gym_rem2d_b200.modules import get_module_list
+from oracle.oracle import OracleEngine
+
+F32 = np.float32
+
+
+def flat_engine(**kw):
+    e = OracleEngine(**kw)
+    xs, ys = terrain.flat_terrain()
+    e.set_terrain(ys, K.TERRAIN_STEP)
+    return e
+
+
+def single(shape, hx, hy, x=5.0, y=7.0, a=0.0):
+    c = CreatureTable()
+    c.shape, c.hx, c.hy, c.x0, c.y0, c.a0 = [shape], [hx], [hy], [x], [y], [a]
+    c.node_index, c.type_ref, c.ctrl = [0], [0], [(0.0, 0.0, 0.0, 0.0, 0.0)]
+    return c
+
+
+def add_child(c, parent, shape, hx, hy, x, y, a, anchor_a, anchor_b, ctrl=(0.0, 0.0, 0.0, 0.0, 0.0)):
+    c.shape.append(shape); c.hx.append(hx); c.hy.append(hy); c.x0.append(x); c.y0.append(y); c.a0.append(a)
+    c.node_index.append(len(c.shape) - 1); c.type_ref.append(0); c.ctrl.append(ctrl)
+    c.joint_parent.append(parent); c.anchor_a.append(anchor_a); c.anchor_b.append(anchor_b)
+    c.lower.append(float(F32(-math.pi / 2))); c.upper.append(float(F32(math.pi / 2))); c.max_torque.append(50.0)
+    return c
+
+
+def test_control_pin_matches_reference_step(golden_dir):
+    pin = json.load(open(os.path.join(golden_dir, "control_pin.json")))
+    random.seed(pin["seed"])
+    g = DirectEncoding(get_module_list())
+    pop = pack([flatten_tree(g.create(8), g.moduleList)])
+    e = flat_engine(dt=0.0)          # dt = 0: Box2D skips Solve/SolveTOI, bodies stay frozen like the fake world
+    e.upload(pop)
+    assert pin["step_args"][1:] == [180, 60] and F32(pin["step_args"][0]) == F32(0.02)
+    for t, ref in enumerate(pin["ticks"]):
+        e.step(1)
+        st = e.read_state()
+        assert np.array_equal(st["motor_speed"], np.array(ref["motor_speed"], F32)), t
+        assert st["wod"][0] == ref["wod"]
+        assert bool(st["alive"][0]) == (not ref["done"])
+    # frozen at x = 5 -> reward 5 -> fitness 5 while alive
+    assert e.fitness()[0] == 5.0
+
+
+def test_free_fall_closed_form():
+    e = flat_engine(terminate=0)
+    e.upload(pack([single(0, 0.25, 0.25, y=9.0)]))
+    y = F32(9.0); v = F32(0.0); dt = F32(0.02)
+    for k in range(20):
+        e.step(1)
+        v = F32(v + F32(dt * F32(-10.0)))       # symplectic Euler in float32, Box2D operation order
+        y = F32(y + F32(dt * v))
+        st = e.read_state()
+        assert st["pose"][0, 1] == y and st["vel"][0, 1] == v and st["pose"][0, 0] == 5.0
+    # closed form y_k = y0 - g dt^2 k(k+1)/2 within float32 accumulation error
+    assert abs(float(y) - (9.0 - 10 * 0.02 ** 2 * 20 * 21 / 2)) < 1e-5
+
+
+def test_box_rests_at_linear_slop_with_two_point_manifold():
+    e = flat_engine(terminate=0)
+    e.upload(pack([single(0, 0.5, 0.25, y=5.5)]))
+    e.step(150)
+    st = e.read_state(max_pairs=8)
+    # polygon skin 0.01 + edge skin 0.01; the position solver only pushes while separation < -linearSlop,
+    # so the box comes to rest with a separation in [-linearSlop, 0]
+    sep = st["pose"][0, 1] - (5.0 + 0.25 + 0.02)
+    assert -0.005 - 1e-4 <= sep <= 1e-4
+    # the box spans three terrain edges; sequential impulses leave a tilt well inside the slop band
+    assert abs(st["pose"][0, 2]) < 0.01 and np.all(np.abs(st["vel"][0]) < 1e-3)
+    assert st["n_touching"][0] >= 1
+    # weight is carried by the normal impulses: sum = m g dt = (4 * .5 * .25) * 10 * 0.02
+    imp = st["touching_impulse"][0][: st["n_touching"][0]]
+    assert abs(imp[:, :2].sum() - 0.5 * 10 * 0.02) < 1e-3
+    e.step(100)
+    assert e.read_state()["awake"][0] == 0          # a lone body at rest goes to sleep after 0.5 s
+
+
+def test_circle_on_interior_vertex_touches_two_edges():
+    e = flat_engine(terminate=0)
+    x_vertex = 10 * K.TERRAIN_STEP
+    e.upload(pack([single(1, 0.3, 0.0, x=x_vertex, y=5.4)]))
+    e.step(120)
+    st = e.read_state(max_pairs=8)
+    pairs = st["touching_pairs"][0][: st["n_touching"][0]]
+    sep = st["pose"][0, 1] - (5.0 + 0.3 + 0.01)
+    assert -0.005 - 1e-4 <= sep <= 1e-4
+    assert st["n_touching"][0] in (1, 2) and set(pairs[:, 1]) <= {9, 10}
+
+
+def _pendulum(ctrl, angle=0.0):
+    # root box far above ground (no contacts in the horizon), child bar hanging from its centre
+    c = single(0, 0.5, 0.5, y=40.0)
+    add_child(c, 0, 0, 0.1, 0.4, 5.0, 40.0 - 0.4, angle, (0.0, 0.0), (0.0, 0.4), ctrl)
+    return c
+
+
+def test_motor_impulse_saturates_at_dt_times_max_torque():
+    e = flat_engine(terminate=0)
+    # huge offset error -> P-controller asks for a speed the 50 N m motor cannot reach in one tick
+    c = _pendulum((0.0, 0.0, 0.0, 1.5, 0.0))
+    c.max_torque[0] = 2.0             # the stock 50 N m never saturates on modules this light
+    e.upload(pack([c]))
+    e.step(1)
+    st = e.read_state()
+    assert st["motor_speed"][0] == F32(1.9 * 1.5)
+    assert st["joint_impulse"][0, 3] == F32(0.02) * F32(2.0)         # clamp at dt * maxMotorTorque
+
+
+def test_limit_snap_from_outside_range():
+    e = flat_engine(terminate=0)
+    e.upload(pack([_pendulum((0.0, 0.0, 0.0, 0.0, 0.0), angle=2.0)]))
+    st0 = e.read_state()
+    e.step(1)
+    st = e.read_state()
+    rel = st["pose"][1, 2] - st["pose"][0, 2]
+    assert st["limit_state"][0] == 2                                  # at upper limit
+    # position solver pulls the angle back by up to 8 degrees per iteration, 60 iterations
+    assert rel <= math.pi / 2 + 2.5 / 180 * math.pi
+
+
+def test_wall_of_death_lifetime_and_fitness_latch():
+    e = flat_engine()
+    e.upload(pack([single(0, 0.25, 0.25)]))
+    e.step(10000)
+    st = e.read_state()
+    # wod = 0.04 k passes x = 5 shortly after tick 125 (double accumulation of 0.04)
+    assert 125 <= st["ticks"][0] <= 127 and st["alive"][0] == 0
+    assert abs(e.fitness()[0] - 5.0) < 1e-3
+
+
+def test_sincos_modes_agree_over_100_ticks():
+    """portable sin/cos (bit-identical to the CUDA build) vs libm sinf/cosf as upstream Box2D uses."""
+    random.seed(11)
+    pop = flatten_population([Individual.random(encoding="direct") for _ in range(16)])
+    xs, ys = terrain.generate_terrain()
+    out = []
+    for mode in (0, 1):
+        e = OracleEngine(sincos_mode=mode)
+        e.set_terrain(ys, K.TERRAIN_STEP)
+        e.upload(pop)
+        e.step(100)
+        out.append(e.read_state()["pose"])
+    err = np.abs(out[0] - out[1]) / np.maximum(1.0, np.abs(out[1]))
+    # chaotic divergence after contact events is expected for a few creatures; the bulk must agree tightly
+    assert np.median(err) < 1e-5
+    assert np.mean(err.max(axis=1) < 1e-4) > 0.7
+
+
+def test_counters_and_threads_are_consistent():
+    random.seed(5)
+    pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(24)])
+    xs, ys = terrain.generate_terrain()
+    res = []
+    for th in (1, 3):
+        e = OracleEngine(threads=th)
+        e.set_terrain(ys, K.TERRAIN_STEP)
+        fit, ticks = e.evaluate(pop, 10000)
+        res.append((fit, ticks, e.counters()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2]
+    assert res[0][2]["ticks"] == int(res[0][1].sum())
+    assert np.all(res[0][1] >= 40)     # the wall of death reaches x = 5 at tick 125; creatures pushed backwards die earlier
