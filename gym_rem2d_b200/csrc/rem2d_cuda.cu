@@ -1,0 +1,658 @@
+// rem2d_cuda.cu — kernels + C-ABI (include/rem2d.h) of the CUDA build, sm_100a only.
+//
+// Host side: sorts creatures into capacity classes (by body count), packs them 32 per batch, keeps one
+// lane-interleaved state block per batch in HBM and launches one CTA (one warp) per batch on one
+// stream per class so small and large classes overlap on the 148 SMs. There is no CPU physics
+// fallback: every tick is computed by rem2d::Sim<...>::tick on the device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rem2d_device.cuh"
+
+using namespace rem2d;
+
+// ------------------------------------------------------------------ capacity classes
+// NB bodies, NC contact-pool slots (fat-AABB overlaps), NT touching contacts staged in shared memory.
+// hot words/lane = 5*NB + 18*(NB-1) + 21*NT; one warp needs 128 B per word.
+#define REM2D_CLASSES(X) \
+    X(0, 2, 12, 4)       \
+    X(1, 4, 24, 6)       \
+    X(2, 8, 40, 10)      \
+    X(3, 12, 56, 14)     \
+    X(4, 16, 72, 18)     \
+    X(5, 22, 96, 24)     \
+    X(6, 32, 128, 34)    \
+    X(7, 44, 160, 34)
+#define N_CLASSES 8
+
+struct ClassInfo { int nb, nc, nt, nj, off_body, off_joint, off_cont, off_edge, words, hot_words; };
+static const ClassInfo g_classes[N_CLASSES] = {
+#define X(i, NB, NC, NT) { NB, NC, NT, Sim<NB, NC, NT>::NJ, Sim<NB, NC, NT>::OFF_BODY, Sim<NB, NC, NT>::OFF_JOINT, \
+                           Sim<NB, NC, NT>::OFF_CONT, Sim<NB, NC, NT>::OFF_EDGE, Sim<NB, NC, NT>::WORDS, Sim<NB, NC, NT>::HOT_WORDS },
+    REM2D_CLASSES(X)
+#undef X
+};
+
+struct DevPop {     // device copy of the flattened table (+ island joint order)
+    const int32_t* body_off; const uint8_t* shape; const float *hx, *hy, *x0, *y0, *a0;
+    const int16_t* joint_parent; const float *anchor_a, *anchor_b, *lower, *upper, *max_torque;
+    const double* ctrl; const uint8_t* joint_order;
+};
+
+// ------------------------------------------------------------------ kernels
+// Build the world of every creature of this class: b2Body/b2Fixture creation (mass data, sweep, proxy fat
+// AABB), joints, controllers, episode scalars. Mirrors oracle world_build()/body_init().
+template <int NB, int NC, int NT>
+__global__ void __launch_bounds__(32) reset_kernel(float* state, const int* __restrict__ lane_creature, DevPop p) {
+    using SimT = Sim<NB, NC, NT>;
+    const int lane = threadIdx.x, batch = blockIdx.x;
+    SimT sim;
+    sim.g = state + (size_t)batch * SimT::WORDS * 32 + lane;
+    const int c = lane_creature[batch * 32 + lane];
+    for (int w = 0; w < S_COUNT; ++w) sim.g[w * 32] = 0.0f;
+    if (c < 0) { sim.setSi(S_NB, 0); sim.setSi(S_ALIVE, 0); return; }
+    const int b0 = p.body_off[c], nb = p.body_off[c + 1] - b0, nj = nb - 1, j0 = b0 - c;
+    sim.nb = nb; sim.nj = nj;
+    sim.setSi(S_NB, nb); sim.setSi(S_NC, 0); sim.setSi(S_ALIVE, 1); sim.setSi(S_TICKS, 0);
+    sim.setSd(S_WOD_LO, 0.0); sim.setSd(S_FIT_LO, 0.0);
+    sim.S(S_INVDT0) = 0.0f; sim.setSi(S_NEWFIX, 1); sim.setSi(S_STATUS, 0); sim.setSi(S_NADV, 0);
+    for (int e = 0; e < RB_MAX_EDGES; ++e) sim.EA(e) = 0.0f;
+    for (int i = 0; i < nb; ++i) {
+        const int shape = p.shape[b0 + i];
+        const float hx = p.hx[b0 + i], hy = p.hy[b0 + i];
+        const float density = 1.0f;
+        float mass, I;
+        V2 center;
+        if (shape == REM2D_SHAPE_CIRCLE) {
+            mass = density * RB_PI * hx * hx;
+            center = mk(0.0f, 0.0f);
+            I = mass * (0.5f * hx * hx + dot(center, center));
+        } else {
+            V2 v[4] = { mk(-hx, -hy), mk(hx, -hy), mk(hx, hy), mk(-hx, hy) };
+            V2 cen = mk(0.0f, 0.0f), s = mk(0.0f, 0.0f);
+            float area = 0.0f, II = 0.0f;
+            for (int q = 0; q < 4; ++q) s = s + v[q];
+            s = (1.0f / 4.0f) * s;
+            const float k_inv3 = 1.0f / 3.0f;
+            for (int q = 0; q < 4; ++q) {
+                V2 e1 = v[q] - s, e2 = q + 1 < 4 ? v[q + 1] - s : v[0] - s;
+                float D = cross(e1, e2);
+                float triangleArea = 0.5f * D;
+                area += triangleArea;
+                cen = cen + (triangleArea * k_inv3) * (e1 + e2);
+                float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
+                float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
+                II += (0.25f * k_inv3 * D) * (intx2 + inty2);
+            }
+            mass = density * area;
+            cen = (1.0f / area) * cen;
+            center = cen + s;
+            I = density * II;
+            I += mass * (dot(center, center) - dot(cen, cen));
+        }
+        float invMass, invI;
+        V2 localCenter = mass * center;
+        if (mass > 0.0f) { invMass = 1.0f / mass; localCenter = invMass * localCenter; }
+        else { mass = 1.0f; invMass = 1.0f; }
+        if (I > 0.0f) { I -= mass * dot(localCenter, localCenter); invI = 1.0f / I; }
+        else { invI = 0.0f; }
+        const float x = p.x0[b0 + i], y = p.y0[b0 + i], a = p.a0[b0 + i];
+        Rot q = rot_set(a);
+        V2 cpos = xmul(mk(x, y), q, localCenter);          // localCenter == 0 for boxes and circles
+        sim.B(BF_CX, i) = cpos.x; sim.B(BF_CY, i) = cpos.y; sim.B(BF_A, i) = a;
+        sim.B(BF_C0X, i) = cpos.x; sim.B(BF_C0Y, i) = cpos.y; sim.B(BF_A0, i) = a; sim.B(BF_ALPHA0, i) = 0.0f;
+        sim.B(BF_VX, i) = 0.0f; sim.B(BF_VY, i) = 0.0f; sim.B(BF_W, i) = 0.0f;
+        sim.B(BF_QS, i) = q.s; sim.B(BF_QC, i) = q.c;
+        sim.B(BF_SLEEP, i) = 0.0f; sim.B(BF_INVM, i) = invMass; sim.B(BF_INVI, i) = invI;
+        sim.B(BF_HX, i) = hx; sim.B(BF_HY, i) = hy;
+        sim.setBi(BF_FLAGS, i, BFL_AWAKE | BFL_MOVED | (shape == REM2D_SHAPE_CIRCLE ? BFL_CIRCLE : 0));
+        V2 lo, hi;
+        sim.shape_aabb(i, mk(x, y), q, lo, hi);
+        sim.B(BF_FLX, i) = lo.x - RB_AABB_EXT; sim.B(BF_FLY, i) = lo.y - RB_AABB_EXT;
+        sim.B(BF_FHX, i) = hi.x + RB_AABB_EXT; sim.B(BF_FHY, i) = hi.y + RB_AABB_EXT;
+    }
+    for (int j = 0; j < nj; ++j) {
+        sim.setJi(JF_META, j, (int)p.joint_parent[j0 + j] | ((int)p.joint_order[j0 + j] << 8));
+        sim.J(JF_LAAX, j) = p.anchor_a[2 * (j0 + j)]; sim.J(JF_LAAY, j) = p.anchor_a[2 * (j0 + j) + 1];
+        sim.J(JF_LABX, j) = p.anchor_b[2 * (j0 + j)]; sim.J(JF_LABY, j) = p.anchor_b[2 * (j0 + j) + 1];
+        sim.J(JF_IMPX, j) = 0.0f; sim.J(JF_IMPY, j) = 0.0f; sim.J(JF_IMPZ, j) = 0.0f; sim.J(JF_MIMP, j) = 0.0f;
+        sim.J(JF_MSPEED, j) = 0.0f; sim.setJi(JF_LIMIT, j, 0);
+        sim.J(JF_LOWER, j) = p.lower[j0 + j]; sim.J(JF_UPPER, j) = p.upper[j0 + j]; sim.J(JF_MAXT, j) = p.max_torque[j0 + j];
+        const double* cc = &p.ctrl[(size_t)(b0 + j + 1) * 5];     // controller of body j+1 drives joint j
+        sim.setJd(JF_AMP, j, cc[0]); sim.setJd(JF_PHASE, j, cc[1]); sim.setJd(JF_FREQ, j, cc[2]);
+        sim.setJd(JF_OFFS, j, cc[3]); sim.setJd(JF_ISTATE, j, cc[4]);
+    }
+}
+
+// One warp per batch of 32 creatures; each lane advances its creature by up to n_ticks ticks.
+template <int NB, int NC, int NT>
+__global__ void __launch_bounds__(32) step_kernel(float* state, int n_ticks, const Terrain* __restrict__ ter,
+                                                  const Consts* __restrict__ k, unsigned long long* counters) {
+    using SimT = Sim<NB, NC, NT>;
+    extern __shared__ float hot[];
+    const int lane = threadIdx.x, batch = blockIdx.x;
+    SimT sim;
+    sim.g = state + (size_t)batch * SimT::WORDS * 32 + lane;
+    sim.h = hot + lane;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
+    if (sim.nb > 0) {
+        for (int t = 0; t < n_ticks; ++t) {
+            if (!sim.Si(S_ALIVE)) break;
+            sim.tick();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
+        unsigned long long v = sim.cnt.c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&counters[i], v);
+    }
+}
+
+// fitness / ticks / alive / status of every creature of a class -> creature-indexed outputs
+__global__ void gather_kernel(const float* state, const int* __restrict__ lane_creature, int n_lanes, int words,
+                              double* fitness, int* ticks, int* alive, int* status) {
+    int gl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= n_lanes) return;
+    int c = lane_creature[gl];
+    if (c < 0) return;
+    const float* g = state + (size_t)(gl >> 5) * words * 32 + (gl & 31);
+    fitness[c] = __hiloint2double(__float_as_int(g[S_FIT_HI * 32]), __float_as_int(g[S_FIT_LO * 32]));
+    ticks[c] = __float_as_int(g[S_TICKS * 32]);
+    alive[c] = __float_as_int(g[S_ALIVE * 32]);
+    status[c] = __float_as_int(g[S_STATUS * 32]);
+}
+
+// ------------------------------------------------------------------ handle
+struct ClassState {
+    std::vector<int> lane_creature;     // host copy: [n_batches*32], -1 = padding lane
+    int n_batches = 0;
+    float* d_state = nullptr;
+    int* d_lane_creature = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
+struct rem2d_handle {
+    rem2d_config cfg;
+    cudaStream_t user_stream = nullptr;
+    Terrain* d_ter = nullptr;
+    Consts* d_consts = nullptr;
+    unsigned long long* d_counters = nullptr;
+    bool have_terrain = false, have_pop = false;
+    int n_edges = 0;
+    // population
+    int n_creatures = 0, n_bodies = 0, n_joints = 0;
+    std::vector<int32_t> body_off;
+    std::vector<int> creature_class, creature_lane;     // lane index within the class (batch*32+lane)
+    void* d_pop_mem[16] = {};
+    DevPop dpop{};
+    ClassState cls[N_CLASSES];
+    double* d_fitness = nullptr; int *d_ticks = nullptr, *d_alive = nullptr, *d_status = nullptr;
+    std::vector<double> h_fitness; std::vector<int> h_ticks, h_alive, h_status;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_fork = nullptr;
+    float last_ms = 0.0f;
+    int64_t launches = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return REM2D_E_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+static void free_population(rem2d_handle* h) {
+    for (auto& p : h->d_pop_mem) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& c : h->cls) {
+        if (c.d_state) cudaFree(c.d_state);
+        if (c.d_lane_creature) cudaFree(c.d_lane_creature);
+        c.d_state = nullptr; c.d_lane_creature = nullptr; c.n_batches = 0; c.lane_creature.clear();
+    }
+    if (h->d_fitness) cudaFree(h->d_fitness);
+    if (h->d_ticks) cudaFree(h->d_ticks);
+    if (h->d_alive) cudaFree(h->d_alive);
+    if (h->d_status) cudaFree(h->d_status);
+    h->d_fitness = nullptr; h->d_ticks = h->d_alive = h->d_status = nullptr;
+    h->have_pop = false;
+}
+
+extern "C" {
+
+void rem2d_default_config(rem2d_config* cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->dt = (float)(1.0 / 50);        // Modular2DEnv.py:26,634
+    cfg->velocity_iterations = 180;     // Modular2DEnv.py:634
+    cfg->position_iterations = 60;
+    cfg->gravity_y = -10.0f;
+    cfg->module_friction = (float)0.1;  // simple_module.py:289
+    cfg->terrain_friction = 2.5f;       // Modular2DEnv.py:62
+    cfg->p_gain = 1.9;                  // Modular2DEnv.py:601
+    cfg->wod_speed = 0.04;              // Modular2DEnv.py:52
+    cfg->env_length = 100.0;            // REM2D_main.py:350
+    cfg->evaluation_steps = 10000;      // REM2D_main.py:350
+    cfg->continuous = 1;
+    cfg->allow_sleep = 1;
+    cfg->terminate = 1;
+    cfg->device = 0;
+    cfg->stream = nullptr;
+    cfg->sincos_mode = 0;
+}
+int rem2d_abi_version(void) { return REM2D_ABI_VERSION; }
+const char* rem2d_backend(void) { return "cuda-sm_100a"; }
+
+int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
+    if (!cfg || !out) { g_create_err = "rem2d_create: NULL argument"; return REM2D_E_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("rem2d_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return REM2D_E_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "rem2d_create: bad device ordinal"; return REM2D_E_INVALID; }
+    if (cfg->sincos_mode != 0) { g_create_err = "rem2d_create: sincos_mode != 0 is an oracle-only option"; return REM2D_E_INVALID; }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return REM2D_E_CUDA; }
+    rem2d_handle* h = new rem2d_handle();
+    h->cfg = *cfg;
+    h->user_stream = (cudaStream_t)cfg->stream;
+    auto fail = [&](const char* what, cudaError_t err) { g_create_err = std::string(what) + ": " + cudaGetErrorString(err); delete h; return REM2D_E_CUDA; };
+    if ((e = cudaMalloc(&h->d_ter, sizeof(Terrain))) != cudaSuccess) return fail("cudaMalloc terrain", e);
+    if ((e = cudaMalloc(&h->d_consts, sizeof(Consts))) != cudaSuccess) return fail("cudaMalloc consts", e);
+    if ((e = cudaMalloc(&h->d_counters, sizeof(unsigned long long) * REM2D_N_COUNTERS)) != cudaSuccess) return fail("cudaMalloc counters", e);
+    cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS);
+    Consts k;
+    k.dt = cfg->dt; k.gravity_y = cfg->gravity_y;
+    k.friction = sqrtf(cfg->terrain_friction * cfg->module_friction);       // b2MixFriction
+    k.vel_iters = cfg->velocity_iterations; k.pos_iters = cfg->position_iterations;
+    k.continuous = cfg->continuous; k.allow_sleep = cfg->allow_sleep; k.terminate = cfg->terminate;
+    k.evaluation_steps = cfg->evaluation_steps;
+    k.p_gain = cfg->p_gain; k.wod_speed = cfg->wod_speed; k.env_length = cfg->env_length;
+    if ((e = cudaMemcpy(h->d_consts, &k, sizeof(k), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy consts", e);
+    for (auto& c : h->cls) {
+        if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    }
+    cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+#define X(i, NB, NC, NT)                                                                                              \
+    if ((e = cudaFuncSetAttribute(step_kernel<NB, NC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                  Sim<NB, NC, NT>::HOT_WORDS * 128)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
+    REM2D_CLASSES(X)
+#undef X
+    *out = h;
+    return REM2D_OK;
+}
+
+int rem2d_destroy(rem2d_handle* h) {
+    if (!h) return REM2D_E_INVALID;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    free_population(h);
+    for (auto& c : h->cls) { if (c.stream) cudaStreamDestroy(c.stream); if (c.done) cudaEventDestroy(c.done); }
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    cudaFree(h->d_ter); cudaFree(h->d_consts); cudaFree(h->d_counters);
+    delete h;
+    return REM2D_OK;
+}
+
+const char* rem2d_last_error(rem2d_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int rem2d_set_terrain(rem2d_handle* h, const double* y, int32_t n, double step) {
+    if (!h) return REM2D_E_INVALID;
+    if (!y || n < 2 || n > RB_MAX_EDGES) { h->err = "set_terrain: need 2..200 vertices"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    Terrain* t = new Terrain();
+    memset(t, 0, sizeof(Terrain));
+    t->n_edges = n - 1;
+    t->step = (float)step;
+    for (int i = 0; i < n - 1; ++i) {
+        // edgeShape vertices: Python doubles -> float32 (Modular2DEnv.py:294-302)
+        float x1 = (float)((double)i * step), y1 = (float)y[i], x2 = (float)((double)(i + 1) * step), y2 = (float)y[i + 1];
+        t->v1x[i] = x1; t->v1y[i] = y1; t->v2x[i] = x2; t->v2y[i] = y2;
+        // b2EdgeShape::ComputeAABB (radius = polygonRadius) + aabbExtension; single float ops, no contraction possible
+        volatile float lox = (x1 < x2 ? x1 : x2), loy = (y1 < y2 ? y1 : y2), hix = (x1 > x2 ? x1 : x2), hiy = (y1 > y2 ? y1 : y2);
+        volatile float a;
+        a = lox - RB_POLY_RADIUS; t->flx[i] = a - RB_AABB_EXT;
+        a = loy - RB_POLY_RADIUS; t->fly[i] = a - RB_AABB_EXT;
+        a = hix + RB_POLY_RADIUS; t->fhx[i] = a + RB_AABB_EXT;
+        a = hiy + RB_POLY_RADIUS; t->fhy[i] = a + RB_AABB_EXT;
+    }
+    cudaError_t e = cudaMemcpy(h->d_ter, t, sizeof(Terrain), cudaMemcpyHostToDevice);
+    delete t;
+    if (e != cudaSuccess) { h->err = std::string("set_terrain: ") + cudaGetErrorString(e); return REM2D_E_CUDA; }
+    h->n_edges = n - 1;
+    h->have_terrain = true;
+    return REM2D_OK;
+}
+
+}  // extern "C"
+
+// joint order inside the creature's island: DFS of b2World::Solve from the newest body, each body's joint
+// list newest first. Pure topology, so it is computed once on the host.
+static void island_joint_order(int nb, const int16_t* parent, uint8_t* order) {
+    int nj = nb - 1;
+    if (nj <= 0) return;
+    std::vector<char> bodyFlag(nb, 0), jointFlag(nj, 0);
+    std::vector<int> stack;
+    stack.push_back(nb - 1);
+    bodyFlag[nb - 1] = 1;
+    int n = 0;
+    while (!stack.empty()) {
+        int b = stack.back();
+        stack.pop_back();
+        for (int j = nj - 1; j >= 0; --j) {
+            if (parent[j] != b && j + 1 != b) continue;
+            if (jointFlag[j]) continue;
+            int other = parent[j] == b ? j + 1 : parent[j];
+            order[n++] = (uint8_t)j;
+            jointFlag[j] = 1;
+            if (bodyFlag[other]) continue;
+            stack.push_back(other);
+            bodyFlag[other] = 1;
+        }
+    }
+}
+
+template <typename T>
+static cudaError_t upload_array(rem2d_handle* h, int slot, const T* src, size_t n, const T** dst) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    h->d_pop_mem[slot] = d;
+    if (n) e = cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->user_stream);
+    *dst = (const T*)d;
+    return e;
+}
+
+static int launch_reset(rem2d_handle* h);
+
+extern "C" int rem2d_upload(rem2d_handle* h, const rem2d_population* pop) {
+    if (!h || !pop) return REM2D_E_INVALID;
+    if (pop->n_creatures < 0 || pop->n_joints != pop->n_bodies - pop->n_creatures) { h->err = "upload: inconsistent counts"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    free_population(h);
+    const int n = pop->n_creatures;
+    h->n_creatures = n; h->n_bodies = pop->n_bodies; h->n_joints = pop->n_joints;
+    h->body_off.assign(pop->body_off, pop->body_off + n + 1);
+    // classify + validate
+    h->creature_class.assign(n, -1);
+    h->creature_lane.assign(n, -1);
+    std::vector<std::vector<int>> members(N_CLASSES);
+    for (int c = 0; c < n; ++c) {
+        int nb = pop->body_off[c + 1] - pop->body_off[c];
+        if (nb < 1) { h->err = "upload: creature without a root body"; return REM2D_E_INVALID; }
+        int k = -1;
+        for (int q = 0; q < N_CLASSES; ++q) if (nb <= g_classes[q].nb) { k = q; break; }
+        if (k < 0) { char buf[128]; snprintf(buf, sizeof(buf), "upload: creature %d has %d bodies (> %d supported)", c, nb, g_classes[N_CLASSES - 1].nb); h->err = buf; return REM2D_E_CAPACITY; }
+        int j0 = pop->body_off[c] - c;
+        for (int j = 0; j < nb - 1; ++j)
+            if (pop->joint_parent[j0 + j] < 0 || pop->joint_parent[j0 + j] > j) { h->err = "upload: joint parent must precede its child"; return REM2D_E_INVALID; }
+        h->creature_class[c] = k;
+        members[k].push_back(c);
+    }
+    std::vector<uint8_t> order((size_t)std::max(pop->n_joints, 1), 0);
+    for (int c = 0; c < n; ++c) {
+        int nb = pop->body_off[c + 1] - pop->body_off[c], j0 = pop->body_off[c] - c;
+        island_joint_order(nb, pop->joint_parent + j0, order.data() + j0);
+    }
+    size_t nbod = (size_t)pop->n_bodies, nj = (size_t)pop->n_joints;
+    CK(upload_array(h, 0, pop->body_off, (size_t)n + 1, &h->dpop.body_off));
+    CK(upload_array(h, 1, pop->shape, nbod, &h->dpop.shape));
+    CK(upload_array(h, 2, pop->hx, nbod, &h->dpop.hx));
+    CK(upload_array(h, 3, pop->hy, nbod, &h->dpop.hy));
+    CK(upload_array(h, 4, pop->x0, nbod, &h->dpop.x0));
+    CK(upload_array(h, 5, pop->y0, nbod, &h->dpop.y0));
+    CK(upload_array(h, 6, pop->a0, nbod, &h->dpop.a0));
+    CK(upload_array(h, 7, pop->joint_parent, nj, &h->dpop.joint_parent));
+    CK(upload_array(h, 8, pop->anchor_a, nj * 2, &h->dpop.anchor_a));
+    CK(upload_array(h, 9, pop->anchor_b, nj * 2, &h->dpop.anchor_b));
+    CK(upload_array(h, 10, pop->lower, nj, &h->dpop.lower));
+    CK(upload_array(h, 11, pop->upper, nj, &h->dpop.upper));
+    CK(upload_array(h, 12, pop->max_torque, nj, &h->dpop.max_torque));
+    CK(upload_array(h, 13, pop->ctrl, nbod * 5, &h->dpop.ctrl));
+    CK(upload_array(h, 14, (const uint8_t*)order.data(), nj, &h->dpop.joint_order));
+    // the pageable source buffers (order, caller arrays) must stay valid until the copies ran
+    CK(cudaStreamSynchronize(h->user_stream));
+    for (int k = 0; k < N_CLASSES; ++k) {
+        auto& m = members[k];
+        if (m.empty()) continue;
+        // big creatures first: batches of similar size limit lane divergence, and the costly batches start early
+        std::stable_sort(m.begin(), m.end(), [&](int a, int b) {
+            return (pop->body_off[a + 1] - pop->body_off[a]) > (pop->body_off[b + 1] - pop->body_off[b]);
+        });
+        ClassState& cs = h->cls[k];
+        cs.n_batches = (int)((m.size() + 31) / 32);
+        cs.lane_creature.assign((size_t)cs.n_batches * 32, -1);
+        for (size_t i = 0; i < m.size(); ++i) { cs.lane_creature[i] = m[i]; h->creature_lane[m[i]] = (int)i; }
+        CK(cudaMalloc(&cs.d_lane_creature, cs.lane_creature.size() * sizeof(int)));
+        CK(cudaMemcpy(cs.d_lane_creature, cs.lane_creature.data(), cs.lane_creature.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&cs.d_state, (size_t)cs.n_batches * g_classes[k].words * 32 * sizeof(float)));
+    }
+    CK(cudaMalloc(&h->d_fitness, sizeof(double) * std::max(n, 1)));
+    CK(cudaMalloc(&h->d_ticks, sizeof(int) * std::max(n, 1)));
+    CK(cudaMalloc(&h->d_alive, sizeof(int) * std::max(n, 1)));
+    CK(cudaMalloc(&h->d_status, sizeof(int) * std::max(n, 1)));
+    h->h_fitness.assign(n, 0.0); h->h_ticks.assign(n, 0); h->h_alive.assign(n, 0); h->h_status.assign(n, 0);
+    h->have_pop = true;
+    return launch_reset(h);
+}
+
+// fork the class streams off the user stream / join them back
+static int fork_streams(rem2d_handle* h) {
+    CK(cudaEventRecord(h->ev_fork, h->user_stream));
+    for (auto& c : h->cls) if (c.n_batches) CK(cudaStreamWaitEvent(c.stream, h->ev_fork, 0));
+    return REM2D_OK;
+}
+static int join_streams(rem2d_handle* h) {
+    for (auto& c : h->cls) if (c.n_batches) { CK(cudaEventRecord(c.done, c.stream)); CK(cudaStreamWaitEvent(h->user_stream, c.done, 0)); }
+    return REM2D_OK;
+}
+
+static int launch_reset(rem2d_handle* h) {
+    if (!h->have_terrain) { h->err = "reset: no terrain set"; return REM2D_E_INVALID; }
+    int rc = fork_streams(h);
+    if (rc) return rc;
+    for (int k = N_CLASSES - 1; k >= 0; --k) {
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches) continue;
+        switch (k) {
+#define X(i, NB, NC, NT) case i: reset_kernel<NB, NC, NT><<<cs.n_batches, 32, 0, cs.stream>>>(cs.d_state, cs.d_lane_creature, h->dpop); break;
+            REM2D_CLASSES(X)
+#undef X
+        }
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    rc = join_streams(h);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
+    return REM2D_OK;
+}
+
+extern "C" int rem2d_reset(rem2d_handle* h) {
+    if (!h) return REM2D_E_INVALID;
+    if (!h->have_pop) { h->err = "reset: no population uploaded"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    return launch_reset(h);
+}
+
+static int gather(rem2d_handle* h) {
+    for (int k = 0; k < N_CLASSES; ++k) {
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches) continue;
+        int n_lanes = cs.n_batches * 32;
+        gather_kernel<<<(n_lanes + 127) / 128, 128, 0, h->user_stream>>>(cs.d_state, cs.d_lane_creature, n_lanes, g_classes[k].words,
+                                                                        h->d_fitness, h->d_ticks, h->d_alive, h->d_status);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    int n = h->n_creatures;
+    CK(cudaMemcpyAsync(h->h_fitness.data(), h->d_fitness, sizeof(double) * n, cudaMemcpyDeviceToHost, h->user_stream));
+    CK(cudaMemcpyAsync(h->h_ticks.data(), h->d_ticks, sizeof(int) * n, cudaMemcpyDeviceToHost, h->user_stream));
+    CK(cudaMemcpyAsync(h->h_alive.data(), h->d_alive, sizeof(int) * n, cudaMemcpyDeviceToHost, h->user_stream));
+    CK(cudaMemcpyAsync(h->h_status.data(), h->d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, h->user_stream));
+    CK(cudaStreamSynchronize(h->user_stream));
+    for (int c = 0; c < n; ++c)
+        if (h->h_status[c]) {
+            char buf[200];
+            snprintf(buf, sizeof(buf), "creature %d exceeded a capacity of its class (status %d: 1 contact pool, 2 touching contacts, 4 TOI island)", c, h->h_status[c]);
+            h->err = buf;
+            return REM2D_E_CAPACITY;
+        }
+    return REM2D_OK;
+}
+
+extern "C" {
+
+int rem2d_step(rem2d_handle* h, int32_t n_ticks) {
+    if (!h) return REM2D_E_INVALID;
+    if (!h->have_pop || n_ticks < 0) { h->err = "step: no population / negative tick count"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    CK(cudaEventRecord(h->ev_start, h->user_stream));
+    int rc = fork_streams(h);
+    if (rc) return rc;
+    for (int k = N_CLASSES - 1; k >= 0; --k) {        // most expensive class first
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches) continue;
+        switch (k) {
+#define X(i, NB, NC, NT)                                                                                             \
+    case i:                                                                                                          \
+        step_kernel<NB, NC, NT><<<cs.n_batches, 32, Sim<NB, NC, NT>::HOT_WORDS * 128, cs.stream>>>(                 \
+            cs.d_state, n_ticks, h->d_ter, h->d_consts, h->d_counters);                                              \
+        break;
+            REM2D_CLASSES(X)
+#undef X
+        }
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    rc = join_streams(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_stop, h->user_stream));
+    CK(cudaEventSynchronize(h->ev_stop));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev_start, h->ev_stop));
+    return REM2D_OK;
+}
+
+int rem2d_fitness(rem2d_handle* h, double* out) {
+    if (!h || !out) return REM2D_E_INVALID;
+    if (!h->have_pop) { h->err = "fitness: no population uploaded"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    int rc = gather(h);
+    if (rc) return rc;
+    memcpy(out, h->h_fitness.data(), sizeof(double) * h->n_creatures);
+    return REM2D_OK;
+}
+
+int rem2d_get_counters(rem2d_handle* h, uint64_t* out) {
+    if (!h || !out) return REM2D_E_INVALID;
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->user_stream));
+    CK(cudaMemcpy(out, h->d_counters, sizeof(unsigned long long) * REM2D_N_COUNTERS, cudaMemcpyDeviceToHost));
+    return REM2D_OK;
+}
+
+int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_ticks, double* fitness_out, int32_t* ticks_out) {
+    int rc = rem2d_upload(h, pop);
+    if (rc) return rc;
+    rc = rem2d_step(h, max_ticks);
+    if (rc) return rc;
+    rc = gather(h);
+    if (rc) return rc;
+    if (fitness_out) memcpy(fitness_out, h->h_fitness.data(), sizeof(double) * h->n_creatures);
+    if (ticks_out) memcpy(ticks_out, h->h_ticks.data(), sizeof(int) * h->n_creatures);
+    return REM2D_OK;
+}
+
+float rem2d_last_step_ms(rem2d_handle* h) { return h ? h->last_ms : 0.0f; }
+int64_t rem2d_launch_count(rem2d_handle* h) { return h ? h->launches : 0; }
+
+// Test/diagnostic path: copies the whole state of every class to the host and decodes it there.
+int rem2d_read_state(rem2d_handle* h, rem2d_state_view* out) {
+    if (!h || !out) return REM2D_E_INVALID;
+    if (!h->have_pop) { h->err = "read_state: no population uploaded"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->user_stream));
+    for (int k = 0; k < N_CLASSES; ++k) {
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches) continue;
+        const ClassInfo& ci = g_classes[k];
+        std::vector<float> st((size_t)cs.n_batches * ci.words * 32);
+        CK(cudaMemcpy(st.data(), cs.d_state, st.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        auto asint = [](float f) { int i; memcpy(&i, &f, 4); return i; };
+        for (size_t gl = 0; gl < cs.lane_creature.size(); ++gl) {
+            int c = cs.lane_creature[gl];
+            if (c < 0) continue;
+            const float* g = st.data() + (gl >> 5) * (size_t)ci.words * 32 + (gl & 31);
+            auto S = [&](int f) { return g[f * 32]; };
+            auto B = [&](int f, int i) { return g[(ci.off_body + f * ci.nb + i) * 32]; };
+            auto J = [&](int f, int j) { return g[(ci.off_joint + f * ci.nj + j) * 32]; };
+            auto C = [&](int f, int q) { return g[(ci.off_cont + f * ci.nc + q) * 32]; };
+            int b0 = h->body_off[c], nb = h->body_off[c + 1] - b0, j0 = b0 - c;
+            int awake = 0;
+            for (int i = 0; i < nb; ++i) {
+                if (out->pose) { out->pose[3 * (b0 + i)] = B(BF_CX, i); out->pose[3 * (b0 + i) + 1] = B(BF_CY, i); out->pose[3 * (b0 + i) + 2] = B(BF_A, i); }
+                if (out->vel) { out->vel[3 * (b0 + i)] = B(BF_VX, i); out->vel[3 * (b0 + i) + 1] = B(BF_VY, i); out->vel[3 * (b0 + i) + 2] = B(BF_W, i); }
+                awake |= asint(B(BF_FLAGS, i)) & BFL_AWAKE;
+            }
+            for (int j = 0; j < nb - 1; ++j) {
+                if (out->joint_impulse) {
+                    float* o = &out->joint_impulse[4 * (j0 + j)];
+                    o[0] = J(JF_IMPX, j); o[1] = J(JF_IMPY, j); o[2] = J(JF_IMPZ, j); o[3] = J(JF_MIMP, j);
+                }
+                if (out->limit_state) out->limit_state[j0 + j] = asint(J(JF_LIMIT, j));
+                if (out->motor_speed) out->motor_speed[j0 + j] = J(JF_MSPEED, j);
+            }
+            if (out->alive) out->alive[c] = asint(S(S_ALIVE));
+            if (out->ticks) out->ticks[c] = asint(S(S_TICKS));
+            if (out->awake) out->awake[c] = awake ? 1 : 0;
+            if (out->wod) { int lo = asint(S(S_WOD_LO)), hi = asint(S(S_WOD_HI)); uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; memcpy(&d, &u, 8); out->wod[c] = d; }
+            int nc = asint(S(S_NC)), ntouch = 0;
+            for (int q = 0; q < nc; ++q) ntouch += ((asint(C(CF_KEY, q)) >> 16) & CK_TOUCHING) ? 1 : 0;
+            if (out->n_contacts) out->n_contacts[c] = nc;
+            if (out->n_touching) out->n_touching[c] = ntouch;
+            if (out->touching_pairs && out->max_pairs > 0) {
+                int32_t* tp = &out->touching_pairs[(size_t)c * out->max_pairs * 2];
+                float* ti = out->touching_impulse ? &out->touching_impulse[(size_t)c * out->max_pairs * 4] : nullptr;
+                for (int q = 0; q < out->max_pairs * 2; ++q) tp[q] = -1;
+                if (ti) for (int q = 0; q < out->max_pairs * 4; ++q) ti[q] = 0.0f;
+                std::vector<std::pair<int, int>> pairs;    // (body<<8 | edge, pool index)
+                for (int q = 0; q < nc; ++q) {
+                    int key = asint(C(CF_KEY, q));
+                    if (!((key >> 16) & CK_TOUCHING)) continue;
+                    pairs.push_back({((key & 0xff) << 8) | ((key >> 8) & 0xff), q});
+                }
+                std::sort(pairs.begin(), pairs.end());
+                for (size_t q = 0; q < pairs.size() && (int)q < out->max_pairs; ++q) {
+                    int pq = pairs[q].second;
+                    int key = asint(C(CF_KEY, pq));
+                    int count = (key >> (16 + CK_COUNT_SHIFT)) & 3;
+                    tp[2 * q] = key & 0xff; tp[2 * q + 1] = (key >> 8) & 0xff;
+                    if (ti) {
+                        ti[4 * q] = C(CF_P0N, pq); ti[4 * q + 1] = count > 1 ? C(CF_P1N, pq) : 0.0f;
+                        ti[4 * q + 2] = C(CF_P0T, pq); ti[4 * q + 3] = count > 1 ? C(CF_P1T, pq) : 0.0f;
+                    }
+                }
+            }
+        }
+    }
+    return REM2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1417 @@
+// rem2d_device.cuh — device code of the batched REM2D step for sm_100a.
+//
+// Mapping: ONE LANE = ONE CREATURE (one Box2D world of the reference), 32 creatures per warp, one warp
+// per CTA. Nothing on this path is a dense contraction, so there are no tensor-core instructions; the
+// per-tick work is a long chain of dependent fp32 operations on ~1 KB of state per creature.
+//
+//  * cold state (poses, sweeps, fat AABBs, contact pool + manifolds, joint definitions, controller state)
+//    lives in HBM in a lane-interleaved block per batch of 32 creatures: word w of lane l is at
+//    block[w*32 + l], so every access with a warp-uniform word index is one coalesced 128-byte line;
+//  * hot state of the two iteration loops (180 velocity iterations, <= 60 position iterations) is staged
+//    in shared memory in the same [word][lane] layout: bank == lane, so the per-lane *divergent* body /
+//    joint / contact indices of different creatures are bank-conflict free by construction.
+//
+// Arithmetic restates Box2D 2.3 (b2World::Step and below) for the reference's scene — see
+// oracle/rem2d_oracle.c for the plain-C restatement this is tested against bit for bit. The terrain
+// side of every contact is a static body with identity transform, which removes all "A" terms
+// (invMassA = invIA = 0, vA = wA = 0, xfA = I) exactly, up to the sign of zeros.
+// Compile with -fmad=false: upstream Box2D builds do not contract multiply-adds.
+//
+// Reference call sites (under /root/reference/ModularER_2D): Modular2DEnv.py:607-653 (step),
+// :600-605 (PID), Controller/m_controller.py:17-21, REM2D_main.py:362-377 (episode loop).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+#include "../../include/rem2d.h"
+
+namespace rem2d {
+
+// ------------------------------------------------------------------ Box2D settings
+#define RB_PI 3.14159265359f
+#define RB_EPS FLT_EPSILON
+#define RB_MAXF FLT_MAX
+#define RB_LINEAR_SLOP 0.005f
+#define RB_ANGULAR_SLOP (2.0f / 180.0f * RB_PI)
+#define RB_POLY_RADIUS (2.0f * RB_LINEAR_SLOP)
+#define RB_AABB_EXT 0.1f
+#define RB_AABB_MULT 2.0f
+#define RB_MAX_LIN_CORR 0.2f
+#define RB_MAX_ANG_CORR (8.0f / 180.0f * RB_PI)
+#define RB_MAX_TRANS 2.0f
+#define RB_MAX_ROT (0.5f * RB_PI)
+#define RB_BAUMGARTE 0.2f
+#define RB_TOI_BAUMGARTE 0.75f
+#define RB_MAX_SUBSTEPS 8
+#define RB_TIME_TO_SLEEP 0.5f
+#define RB_LIN_SLEEP_TOL 0.01f
+#define RB_ANG_SLEEP_TOL (2.0f / 180.0f * RB_PI)
+#define RB_MAX_POLY_VERTS 16   // pybox2d build value; bounds the TOI push-back loop only
+
+#define RB_MAX_EDGES 200       // terrain edges (199 used)
+#define RB_TOI_ISLAND_CAP 12   // touching contacts of ONE module in a TOI mini-island
+
+struct V2 { float x, y; };
+struct Rot { float s, c; };
+
+__device__ __forceinline__ V2 mk(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ V2 operator-(V2 a) { return mk(-a.x, -a.y); }
+__device__ __forceinline__ V2 operator*(float s, V2 a) { return mk(s * a.x, s * a.y); }
+__device__ __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ V2 cross_vs(V2 a, float s) { return mk(s * a.y, -s * a.x); }
+__device__ __forceinline__ V2 cross_sv(float s, V2 a) { return mk(-s * a.y, s * a.x); }
+__device__ __forceinline__ float len(V2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ float min2(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float max2(float a, float b) { return a > b ? a : b; }
+__device__ __forceinline__ float clampf(float a, float lo, float hi) { return max2(lo, min2(a, hi)); }
+__device__ __forceinline__ float abs2(float a) { return a > 0.0f ? a : -a; }
+__device__ __forceinline__ float normalize(V2& a) {
+    float l = len(a);
+    if (l < RB_EPS) return 0.0f;
+    float inv = 1.0f / l;
+    a.x *= inv; a.y *= inv;
+    return l;
+}
+__device__ __forceinline__ V2 rmul(Rot q, V2 v) { return mk(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
+__device__ __forceinline__ V2 rmulT(Rot q, V2 v) { return mk(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
+// b2Mul(xf, v) with xf = (p, q)
+__device__ __forceinline__ V2 xmul(V2 p, Rot q, V2 v) {
+    return mk((q.c * v.x - q.s * v.y) + p.x, (q.s * v.x + q.c * v.y) + p.y);
+}
+__device__ __forceinline__ V2 xmulT(V2 p, Rot q, V2 v) {
+    float px = v.x - p.x, py = v.y - p.y;
+    return mk(q.c * px + q.s * py, -q.s * px + q.c * py);
+}
+
+// ------------------------------------------------------------------ portable sin/cos
+// Same operation sequence as oracle/rem2d_oracle.c:sincos_kernel (double precision, no contraction):
+// 3-term Cody-Waite reduction by pi/2 + degree-13/14 minimax kernels, result rounded to float.
+__device__ __forceinline__ void sincos_kernel(double x, double& s, double& c) {
+    const double PIO2_1 = 1.57079632673412561417e+00, PIO2_2 = 6.07710050630396597660e-11,
+                 PIO2_2T = 2.02226624879595063154e-21, TWO_OVER_PI = 6.36619772367581382433e-01;
+    double kd = floor(x * TWO_OVER_PI + 0.5);
+    double r = ((x - kd * PIO2_1) - kd * PIO2_2) - kd * PIO2_2T;
+    double z = r * r;
+    double ps = -1.66666666666666324348e-01 + z * (8.33333333332248946124e-03 + z * (-1.98412698298579493134e-04 +
+                z * (2.75573137070700676789e-06 + z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10))));
+    double pc = 4.16666666666666019037e-02 + z * (-1.38888888888741095749e-03 + z * (2.48015872894767294178e-05 +
+                z * (-2.75573143513906633035e-07 + z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11))));
+    double sr = r + (r * z) * ps;
+    double cr = (1.0 - 0.5 * z) + (z * z) * pc;
+    long long n = (long long)kd & 3LL;
+    if (n == 0) { s = sr; c = cr; }
+    else if (n == 1) { s = cr; c = -sr; }
+    else if (n == 2) { s = -sr; c = -cr; }
+    else { s = -cr; c = sr; }
+}
+__device__ __forceinline__ Rot rot_set(float a) {
+    double s, c;
+    sincos_kernel((double)a, s, c);
+    Rot q; q.s = (float)s; q.c = (float)c;
+    return q;
+}
+
+// ------------------------------------------------------------------ cold state layout (words per lane)
+enum { S_NB, S_NC, S_ALIVE, S_TICKS, S_WOD_LO, S_WOD_HI, S_FIT_LO, S_FIT_HI, S_INVDT0, S_NEWFIX, S_STATUS,
+       S_NADV, S_ADV0, S_COUNT = S_ADV0 + 8 };
+enum { BF_CX, BF_CY, BF_A, BF_VX, BF_VY, BF_W, BF_C0X, BF_C0Y, BF_A0, BF_ALPHA0, BF_QS, BF_QC,
+       BF_FLX, BF_FLY, BF_FHX, BF_FHY, BF_SLEEP, BF_INVM, BF_INVI, BF_HX, BF_HY, BF_FLAGS, BF_COUNT };
+enum { JF_META, JF_LAAX, JF_LAAY, JF_LABX, JF_LABY, JF_IMPX, JF_IMPY, JF_IMPZ, JF_MIMP, JF_MSPEED, JF_LIMIT,
+       JF_LOWER, JF_UPPER, JF_MAXT, JF_AMP, JF_PHASE = JF_AMP + 2, JF_FREQ = JF_PHASE + 2, JF_OFFS = JF_FREQ + 2,
+       JF_ISTATE = JF_OFFS + 2, JF_COUNT = JF_ISTATE + 2 };
+enum { CF_KEY, CF_TOI, CF_LNX, CF_LNY, CF_LPX, CF_LPY, CF_P0X, CF_P0Y, CF_P0N, CF_P0T, CF_P0ID,
+       CF_P1X, CF_P1Y, CF_P1N, CF_P1T, CF_P1ID, CF_COUNT };
+
+// body flags
+#define BFL_AWAKE 1
+#define BFL_MOVED 2
+#define BFL_ISLAND 4
+#define BFL_CIRCLE 8
+// contact key: body | edge << 8 | flags << 16 | toiCount << 24
+#define CK_ENABLED 0x01
+#define CK_TOUCHING 0x02
+#define CK_ISLAND 0x04
+#define CK_TOIFLAG 0x08
+#define CK_TYPE_SHIFT 4      // 2 bits: manifold type
+#define CK_COUNT_SHIFT 6     // 2 bits: manifold pointCount
+#define MT_CIRCLES 0
+#define MT_FACE_A 1
+#define MT_FACE_B 2
+// status bits
+#define ST_POOL_OVERFLOW 1     // contact pool (NC) exhausted
+#define ST_HOT_OVERFLOW 2      // touching-contact capacity of the shared-memory stage (NT) exhausted
+#define ST_TOI_OVERFLOW 4      // TOI mini-island larger than RB_TOI_ISLAND_CAP
+
+// hot (shared memory) layout, words per lane: 5*NB + 18*NJ + 21*NT
+enum { HB_VX, HB_VY, HB_W, HB_INVM, HB_INVI, HB_COUNT };                 // position phase: CX, CY, A reuse 0..2
+enum { HJ_META, HJ_RAX, HJ_RAY, HJ_RBX, HJ_RBY, HJ_EXX, HJ_EYX, HJ_EZX, HJ_EYY, HJ_EZY, HJ_EZZ, HJ_MMASS,
+       HJ_IMPX, HJ_IMPY, HJ_IMPZ, HJ_MIMP, HJ_MSPEED, HJ_MAXIMP, HJ_COUNT };
+// position-phase overlay of a joint slot
+enum { PJ_META = HJ_META, PJ_LAAX, PJ_LAAY, PJ_LABX, PJ_LABY, PJ_LOWER, PJ_UPPER };
+enum { HC_META, HC_NX, HC_NY, HC_R0X, HC_R0Y, HC_NM0, HC_TM0, HC_NI0, HC_TI0, HC_R1X, HC_R1Y, HC_NM1, HC_TM1,
+       HC_NI1, HC_TI1, HC_K11, HC_K12, HC_K22, HC_IXX, HC_IXY, HC_IYY, HC_COUNT };
+// position-phase overlay of a contact slot
+enum { PC_META = HC_META, PC_LNX, PC_LNY, PC_LPX, PC_LPY, PC_P0X, PC_P0Y, PC_P1X, PC_P1Y, PC_RADB };
+
+struct Terrain {           // read-only, shared by every creature (Modular2DEnv.py:294-306)
+    float v1x[RB_MAX_EDGES], v1y[RB_MAX_EDGES], v2x[RB_MAX_EDGES], v2y[RB_MAX_EDGES];
+    float flx[RB_MAX_EDGES], fly[RB_MAX_EDGES], fhx[RB_MAX_EDGES], fhy[RB_MAX_EDGES];   // fat AABBs of the edge proxies
+    int n_edges;
+    float step;
+};
+
+struct Consts {
+    float dt, gravity_y, friction;   // friction = sqrtf(module * terrain)
+    int vel_iters, pos_iters, continuous, allow_sleep, terminate, evaluation_steps;
+    double p_gain, wod_speed, env_length;
+};
+
+// work counters kept in registers and flushed once per launch
+struct Cnt { unsigned int c[REM2D_N_COUNTERS]; };   // per lane per launch; summed into 64-bit totals
+
+template <int NB, int NC, int NT>
+struct Sim {
+    static constexpr int NJ = NB - 1 > 0 ? NB - 1 : 1;
+    static constexpr int OFF_BODY = S_COUNT;
+    static constexpr int OFF_JOINT = OFF_BODY + BF_COUNT * NB;
+    static constexpr int OFF_CONT = OFF_JOINT + JF_COUNT * NJ;
+    static constexpr int OFF_EDGE = OFF_CONT + CF_COUNT * NC;      // alpha0 of the static edge bodies
+    static constexpr int WORDS = OFF_EDGE + RB_MAX_EDGES;
+    static constexpr int HOFF_JOINT = HB_COUNT * NB;
+    static constexpr int HOFF_CONT = HOFF_JOINT + HJ_COUNT * NJ;
+    static constexpr int HOT_WORDS = HOFF_CONT + HC_COUNT * NT;
+
+    float* g;                 // cold block of this batch, already offset by lane
+    float* h;                 // hot block of this warp in shared memory, already offset by lane
+    const Terrain* __restrict__ ter;
+    const Consts* __restrict__ k;
+    Cnt cnt;
+    int nb, nj;
+
+    // ---- accessors
+    __device__ __forceinline__ float& S(int f) { return g[f * 32]; }
+    __device__ __forceinline__ int Si(int f) { return __float_as_int(g[f * 32]); }
+    __device__ __forceinline__ void setSi(int f, int v) { g[f * 32] = __int_as_float(v); }
+    __device__ __forceinline__ double Sd(int f) { return __hiloint2double(Si(f + 1), Si(f)); }
+    __device__ __forceinline__ void setSd(int f, double v) { setSi(f, __double2loint(v)); setSi(f + 1, __double2hiint(v)); }
+    __device__ __forceinline__ float& B(int f, int i) { return g[(OFF_BODY + f * NB + i) * 32]; }
+    __device__ __forceinline__ int Bi(int f, int i) { return __float_as_int(B(f, i)); }
+    __device__ __forceinline__ void setBi(int f, int i, int v) { B(f, i) = __int_as_float(v); }
+    __device__ __forceinline__ float& J(int f, int j) { return g[(OFF_JOINT + f * NJ + j) * 32]; }
+    __device__ __forceinline__ int Ji(int f, int j) { return __float_as_int(J(f, j)); }
+    __device__ __forceinline__ void setJi(int f, int j, int v) { J(f, j) = __int_as_float(v); }
+    __device__ __forceinline__ double Jd(int f, int j) { return __hiloint2double(Ji(f + 1, j), Ji(f, j)); }
+    __device__ __forceinline__ void setJd(int f, int j, double v) { setJi(f, j, __double2loint(v)); setJi(f + 1, j, __double2hiint(v)); }
+    __device__ __forceinline__ float& C(int f, int c) { return g[(OFF_CONT + f * NC + c) * 32]; }
+    __device__ __forceinline__ int Ci(int f, int c) { return __float_as_int(C(f, c)); }
+    __device__ __forceinline__ void setCi(int f, int c, int v) { C(f, c) = __int_as_float(v); }
+    __device__ __forceinline__ float& EA(int e) { return g[(OFF_EDGE + e) * 32]; }
+    __device__ __forceinline__ float& HB(int f, int i) { return h[(f * NB + i) * 32]; }
+    __device__ __forceinline__ float& HJ(int f, int j) { return h[(HOFF_JOINT + f * NJ + j) * 32]; }
+    __device__ __forceinline__ int HJi(int f, int j) { return __float_as_int(HJ(f, j)); }
+    __device__ __forceinline__ float& HC(int f, int c) { return h[(HOFF_CONT + f * NT + c) * 32]; }
+    __device__ __forceinline__ int HCi(int f, int c) { return __float_as_int(HC(f, c)); }
+
+    __device__ __forceinline__ int key_body(int key) { return key & 0xff; }
+    __device__ __forceinline__ int key_edge(int key) { return (key >> 8) & 0xff; }
+    __device__ __forceinline__ int key_flags(int key) { return (key >> 16) & 0xff; }
+    __device__ __forceinline__ int key_toicount(int key) { return (key >> 24) & 0xff; }
+
+    // ---- bodies
+    __device__ __forceinline__ void set_awake(int b, bool flag) {
+        int fl = Bi(BF_FLAGS, b);
+        if (flag) {
+            if (!(fl & BFL_AWAKE)) { setBi(BF_FLAGS, b, fl | BFL_AWAKE); B(BF_SLEEP, b) = 0.0f; }
+        } else {
+            setBi(BF_FLAGS, b, fl & ~BFL_AWAKE);
+            B(BF_SLEEP, b) = 0.0f;
+            B(BF_VX, b) = 0.0f; B(BF_VY, b) = 0.0f; B(BF_W, b) = 0.0f;
+        }
+    }
+    __device__ __forceinline__ void sync_transform(int b) {     // localCenter == 0: xf.p == sweep.c
+        Rot q = rot_set(B(BF_A, b));
+        B(BF_QS, b) = q.s; B(BF_QC, b) = q.c;
+    }
+    // tight AABB of the shape at pose (p, q)   (b2PolygonShape/b2CircleShape::ComputeAABB)
+    __device__ __forceinline__ void shape_aabb(int b, V2 p, Rot q, V2& lo, V2& hi) {
+        float hx = B(BF_HX, b), hy = B(BF_HY, b);
+        if (Bi(BF_FLAGS, b) & BFL_CIRCLE) {
+            V2 z = mk(0.0f, 0.0f);
+            V2 c = p + rmul(q, z);
+            lo = mk(c.x - hx, c.y - hx); hi = mk(c.x + hx, c.y + hx);
+            return;
+        }
+        V2 v0 = xmul(p, q, mk(-hx, -hy));
+        lo = v0; hi = v0;
+        V2 v;
+        v = xmul(p, q, mk(hx, -hy)); lo = mk(min2(lo.x, v.x), min2(lo.y, v.y)); hi = mk(max2(hi.x, v.x), max2(hi.y, v.y));
+        v = xmul(p, q, mk(hx, hy));  lo = mk(min2(lo.x, v.x), min2(lo.y, v.y)); hi = mk(max2(hi.x, v.x), max2(hi.y, v.y));
+        v = xmul(p, q, mk(-hx, hy)); lo = mk(min2(lo.x, v.x), min2(lo.y, v.y)); hi = mk(max2(hi.x, v.x), max2(hi.y, v.y));
+        lo = mk(lo.x - RB_POLY_RADIUS, lo.y - RB_POLY_RADIUS);
+        hi = mk(hi.x + RB_POLY_RADIUS, hi.y + RB_POLY_RADIUS);
+    }
+    // b2Body::SynchronizeFixtures -> b2DynamicTree::MoveProxy (fat AABB rule)
+    __device__ void synchronize_fixtures(int b) {
+        Rot q1 = rot_set(B(BF_A0, b));
+        V2 p1 = mk(B(BF_C0X, b), B(BF_C0Y, b));
+        V2 p2 = mk(B(BF_CX, b), B(BF_CY, b));
+        Rot q2; q2.s = B(BF_QS, b); q2.c = B(BF_QC, b);
+        V2 lo1, hi1, lo2, hi2;
+        shape_aabb(b, p1, q1, lo1, hi1);
+        shape_aabb(b, p2, q2, lo2, hi2);
+        V2 lo = mk(min2(lo1.x, lo2.x), min2(lo1.y, lo2.y)), hi = mk(max2(hi1.x, hi2.x), max2(hi1.y, hi2.y));
+        V2 disp = p2 - p1;
+        float flx = B(BF_FLX, b), fly = B(BF_FLY, b), fhx = B(BF_FHX, b), fhy = B(BF_FHY, b);
+        if (flx <= lo.x && fly <= lo.y && hi.x <= fhx && hi.y <= fhy) return;
+        lo = mk(lo.x - RB_AABB_EXT, lo.y - RB_AABB_EXT);
+        hi = mk(hi.x + RB_AABB_EXT, hi.y + RB_AABB_EXT);
+        V2 d = RB_AABB_MULT * disp;
+        if (d.x < 0.0f) lo.x += d.x; else hi.x += d.x;
+        if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
+        B(BF_FLX, b) = lo.x; B(BF_FLY, b) = lo.y; B(BF_FHX, b) = hi.x; B(BF_FHY, b) = hi.y;
+        setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) | BFL_MOVED);
+    }
+    __device__ __forceinline__ bool overlap_edge(int e, int b) {
+        float alx = __ldg(&ter->flx[e]), aly = __ldg(&ter->fly[e]), ahx = __ldg(&ter->fhx[e]), ahy = __ldg(&ter->fhy[e]);
+        float blx = B(BF_FLX, b), bly = B(BF_FLY, b), bhx = B(BF_FHX, b), bhy = B(BF_FHY, b);
+        float d1x = blx - ahx, d1y = bly - ahy, d2x = alx - bhx, d2y = aly - bhy;
+        if (d1x > 0.0f || d1y > 0.0f) return false;
+        if (d2x > 0.0f || d2y > 0.0f) return false;
+        return true;
+    }
+
+    // ---- contact pool (creation order; index nc-1 is the newest == head of Box2D's lists)
+    __device__ int find_contact(int nc, int b, int e) {
+        int want = b | (e << 8);
+        for (int i = 0; i < nc; ++i)
+            if ((Ci(CF_KEY, i) & 0xffff) == want) return i;
+        return -1;
+    }
+    // b2ContactManager::FindNewContacts: new pairs in ascending (edge, body) order, each becomes the newest
+    __device__ void find_new_contacts() {
+        int elo = ter->n_edges, ehi = -1;
+        int any = 0;
+        for (int b = 0; b < nb; ++b) {
+            if (!(Bi(BF_FLAGS, b) & BFL_MOVED)) continue;
+            any = 1;
+            double l = floor(((double)B(BF_FLX, b) - 0.25) / (double)ter->step) - 1.0;
+            double u = ceil(((double)B(BF_FHX, b) + 0.25) / (double)ter->step) + 1.0;
+            int il = l < 0.0 ? 0 : (l > (double)(ter->n_edges - 1) ? ter->n_edges : (int)l);
+            int iu = u < 0.0 ? -1 : (u > (double)(ter->n_edges - 1) ? ter->n_edges - 1 : (int)u);
+            if (il < elo) elo = il;
+            if (iu > ehi) ehi = iu;
+        }
+        if (!any) return;
+        int nc = Si(S_NC);
+        for (int e = elo; e <= ehi; ++e) {
+            for (int b = 0; b < nb; ++b) {
+                if (!(Bi(BF_FLAGS, b) & BFL_MOVED)) continue;
+                if (!overlap_edge(e, b)) continue;
+                if (find_contact(nc, b, e) >= 0) continue;
+                if (nc == NC) { setSi(S_STATUS, Si(S_STATUS) | ST_POOL_OVERFLOW); continue; }
+                setCi(CF_KEY, nc, b | (e << 8) | (CK_ENABLED << 16));
+                C(CF_TOI, nc) = 1.0f;
+                C(CF_P0N, nc) = 0.0f; C(CF_P0T, nc) = 0.0f; C(CF_P1N, nc) = 0.0f; C(CF_P1T, nc) = 0.0f;
+                ++nc;
+                set_awake(b, true);
+            }
+        }
+        setSi(S_NC, nc);
+        for (int b = 0; b < nb; ++b) setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) & ~BFL_MOVED);
+    }
+    __device__ void destroy_contact(int i) {
+        int nc = Si(S_NC);
+        int key = Ci(CF_KEY, i);
+        if ((key_flags(key) >> CK_COUNT_SHIFT) & 3) set_awake(key_body(key), true);
+        for (int k = i; k < nc - 1; ++k)
+            for (int f = 0; f < CF_COUNT; ++f) C(f, k) = C(f, k + 1);
+        setSi(S_NC, nc - 1);
+    }
+
+    // ---- narrow phase. Edge frame == world frame (static body at the origin).
+    struct Clip { V2 v; int id; };   // id = indexA | indexB<<8 | typeA<<16 | typeB<<24  (vertex 0, face 1)
+    __device__ __forceinline__ int mkid(int ia, int ib, int ta, int tb) { return ia | (ib << 8) | (ta << 16) | (tb << 24); }
+    __device__ __forceinline__ int clip_segment(Clip out[2], const Clip in[2], V2 normal, float offset, int vertexIndexA) {
+        int n = 0;
+        float d0 = dot(normal, in[0].v) - offset;
+        float d1 = dot(normal, in[1].v) - offset;
+        if (d0 <= 0.0f) out[n++] = in[0];
+        if (d1 <= 0.0f) out[n++] = in[1];
+        if (d0 * d1 < 0.0f) {
+            float interp = d0 / (d0 - d1);
+            out[n].v = in[0].v + interp * (in[1].v - in[0].v);
+            out[n].id = mkid(vertexIndexA, (in[0].id >> 8) & 0xff, 0, 1);
+            ++n;
+        }
+        return n;
+    }
+
+    // Evaluate the manifold of contact c at the body's current transform and write it to the pool
+    // (b2Contact::Update incl. warm-start impulse matching by feature id).
+    __device__ void contact_update(int c) {
+        cnt.c[REM2D_CNT_NARROW]++;
+        int key = Ci(CF_KEY, c);
+        int b = key_body(key), e = key_edge(key);
+        int flags = key_flags(key);
+        int oldCount = (flags >> CK_COUNT_SHIFT) & 3;
+        int oldId0 = Ci(CF_P0ID, c), oldId1 = Ci(CF_P1ID, c);
+        float oldN0 = C(CF_P0N, c), oldT0 = C(CF_P0T, c), oldN1 = C(CF_P1N, c), oldT1 = C(CF_P1T, c);
+        bool wasTouching = (flags & CK_TOUCHING) != 0;
+        flags |= CK_ENABLED;
+        V2 v1 = mk(__ldg(&ter->v1x[e]), __ldg(&ter->v1y[e])), v2 = mk(__ldg(&ter->v2x[e]), __ldg(&ter->v2y[e]));
+        V2 p = mk(B(BF_CX, b), B(BF_CY, b));
+        Rot q; q.s = B(BF_QS, b); q.c = B(BF_QC, b);
+        int type = 0, count = 0;
+        V2 ln = mk(0.0f, 0.0f), lp = mk(0.0f, 0.0f), pt[2];
+        int pid[2];
+        pt[0] = pt[1] = mk(0.0f, 0.0f); pid[0] = pid[1] = 0;
+        if (Bi(BF_FLAGS, b) & BFL_CIRCLE) {
+            // b2CollideEdgeAndCircle, circle centre m_p = 0 -> Q = xfB.p
+            float rad = RB_POLY_RADIUS + B(BF_HX, b);
+            V2 Q = p, A = v1, Bv = v2, ee = Bv - A;
+            float u = dot(ee, Bv - Q), v = dot(ee, Q - A);
+            if (v <= 0.0f) {
+                V2 d = Q - A; float dd = dot(d, d);
+                if (!(dd > rad * rad)) { count = 1; type = MT_CIRCLES; lp = A; pid[0] = mkid(0, 0, 0, 0); }
+            } else if (u <= 0.0f) {
+                V2 d = Q - Bv; float dd = dot(d, d);
+                if (!(dd > rad * rad)) { count = 1; type = MT_CIRCLES; lp = Bv; pid[0] = mkid(1, 0, 0, 0); }
+            } else {
+                float den = dot(ee, ee);
+                V2 P = (1.0f / den) * (u * A + v * Bv);
+                V2 d = Q - P; float dd = dot(d, d);
+                if (!(dd > rad * rad)) {
+                    V2 n = mk(-ee.y, ee.x);
+                    if (dot(n, Q - A) < 0.0f) n = mk(-n.x, -n.y);
+                    normalize(n);
+                    count = 1; type = MT_FACE_A; ln = n; lp = A; pid[0] = mkid(0, 0, 1, 0);
+                }
+            }
+        } else {
+            // b2CollideEdgeAndPolygon (b2EPCollider) without ghost vertices; xf = xfB
+            float hx = B(BF_HX, b), hy = B(BF_HY, b);
+            V2 lv[4] = { mk(-hx, -hy), mk(hx, -hy), mk(hx, hy), mk(-hx, hy) };
+            V2 lnrm[4] = { mk(0.0f, -1.0f), mk(1.0f, 0.0f), mk(0.0f, 1.0f), mk(-1.0f, 0.0f) };
+            V2 centroidB = xmul(p, q, mk(0.0f, 0.0f));
+            V2 edge1 = v2 - v1;
+            normalize(edge1);
+            V2 normal1 = mk(edge1.y, -edge1.x);
+            float offset1 = dot(normal1, centroidB - v1);
+            bool front = offset1 >= 0.0f;
+            V2 normal = front ? normal1 : -normal1;
+            V2 pv[4], pn[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pv[i] = xmul(p, q, lv[i]); pn[i] = rmul(q, lnrm[i]); }
+            const float radius = 2.0f * RB_POLY_RADIUS;
+            float edgeSep = RB_MAXF;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { float s = dot(normal, pv[i] - v1); if (s < edgeSep) edgeSep = s; }
+            bool hit = !(edgeSep > radius);
+            int polyIndex = -1; float polySep = -RB_MAXF; bool polyKnown = false;
+            if (hit) {
+                for (int i = 0; i < 4; ++i) {
+                    V2 n = -pn[i];
+                    float s1 = dot(n, pv[i] - v1), s2 = dot(n, pv[i] - v2);
+                    float s = min2(s1, s2);
+                    if (s > radius) { polyKnown = true; polyIndex = i; polySep = s; break; }
+                    // the adjacency test of b2EPCollider can never reject without ghost vertices:
+                    // dot(n - (-normal), normal) = dot(n, normal) + 1 >= 0 > -angularSlop
+                    if (s > polySep) { polyKnown = true; polyIndex = i; polySep = s; }
+                }
+                if (polyKnown && polySep > radius) hit = false;
+            }
+            if (hit) {
+                bool primaryPoly = polyKnown && (polySep > 0.98f * edgeSep + 0.001f);
+                Clip ie[2];
+                int rf_i1, rf_i2; V2 rf_v1, rf_v2, rf_n;
+                if (!primaryPoly) {
+                    type = MT_FACE_A;
+                    int best = 0; float bestValue = dot(normal, pn[0]);
+                    for (int i = 1; i < 4; ++i) { float value = dot(normal, pn[i]); if (value < bestValue) { bestValue = value; best = i; } }
+                    int i1 = best, i2 = i1 + 1 < 4 ? i1 + 1 : 0;
+                    ie[0].v = pv[i1]; ie[0].id = mkid(0, i1, 1, 0);
+                    ie[1].v = pv[i2]; ie[1].id = mkid(0, i2, 1, 0);
+                    if (front) { rf_i1 = 0; rf_i2 = 1; rf_v1 = v1; rf_v2 = v2; rf_n = normal1; }
+                    else { rf_i1 = 1; rf_i2 = 0; rf_v1 = v2; rf_v2 = v1; rf_n = -normal1; }
+                } else {
+                    type = MT_FACE_B;
+                    ie[0].v = v1; ie[0].id = mkid(0, polyIndex, 0, 1);
+                    ie[1].v = v2; ie[1].id = mkid(0, polyIndex, 0, 1);
+                    rf_i1 = polyIndex; rf_i2 = rf_i1 + 1 < 4 ? rf_i1 + 1 : 0;
+                    rf_v1 = pv[rf_i1]; rf_v2 = pv[rf_i2]; rf_n = pn[rf_i1];
+                }
+                V2 side1 = mk(rf_n.y, -rf_n.x), side2 = -side1;
+                float so1 = dot(side1, rf_v1), so2 = dot(side2, rf_v2);
+                Clip cp1[2], cp2[2];
+                int np = clip_segment(cp1, ie, side1, so1, rf_i1);
+                if (np >= 2) np = clip_segment(cp2, cp1, side2, so2, rf_i2);
+                if (np >= 2) {
+                    if (!primaryPoly) { ln = rf_n; lp = rf_v1; }
+                    else { ln = lnrm[rf_i1]; lp = lv[rf_i1]; }
+                    for (int i = 0; i < 2; ++i) {
+                        float separation = dot(rf_n, cp2[i].v - rf_v1);
+                        if (separation <= radius) {
+                            if (!primaryPoly) { pt[count] = xmulT(p, q, cp2[i].v); pid[count] = cp2[i].id; }
+                            else {
+                                pt[count] = cp2[i].v;
+                                int id = cp2[i].id;
+                                pid[count] = mkid((id >> 8) & 0xff, id & 0xff, (id >> 24) & 0xff, (id >> 16) & 0xff);
+                            }
+                            ++count;
+                        }
+                    }
+                }
+            }
+        }
+        // impulse matching by feature id
+        float n0 = 0.0f, t0 = 0.0f, n1 = 0.0f, t1 = 0.0f;
+        if (count > 0) {
+            if (oldCount > 0 && oldId0 == pid[0]) { n0 = oldN0; t0 = oldT0; }
+            else if (oldCount > 1 && oldId1 == pid[0]) { n0 = oldN1; t0 = oldT1; }
+        }
+        if (count > 1) {
+            if (oldCount > 0 && oldId0 == pid[1]) { n1 = oldN0; t1 = oldT0; }
+            else if (oldCount > 1 && oldId1 == pid[1]) { n1 = oldN1; t1 = oldT1; }
+        }
+        bool touching = count > 0;
+        if (touching != wasTouching) set_awake(b, true);
+        flags &= ~(CK_TOUCHING | (3 << CK_TYPE_SHIFT) | (3 << CK_COUNT_SHIFT));
+        if (touching) flags |= CK_TOUCHING;
+        flags |= (type << CK_TYPE_SHIFT) | (count << CK_COUNT_SHIFT);
+        setCi(CF_KEY, c, (key & 0xff00ffff) | (flags << 16));
+        if (count > 0) {
+            C(CF_LNX, c) = ln.x; C(CF_LNY, c) = ln.y; C(CF_LPX, c) = lp.x; C(CF_LPY, c) = lp.y;
+            C(CF_P0X, c) = pt[0].x; C(CF_P0Y, c) = pt[0].y; C(CF_P0N, c) = n0; C(CF_P0T, c) = t0; setCi(CF_P0ID, c, pid[0]);
+        }
+        if (count > 1) {
+            C(CF_P1X, c) = pt[1].x; C(CF_P1Y, c) = pt[1].y; C(CF_P1N, c) = n1; C(CF_P1T, c) = t1; setCi(CF_P1ID, c, pid[1]);
+        }
+    }
+
+    // b2ContactManager::Collide, newest contact first
+    __device__ void collide() {
+        for (int i = Si(S_NC) - 1; i >= 0; --i) {
+            int key = Ci(CF_KEY, i);
+            int b = key_body(key);
+            if (!(Bi(BF_FLAGS, b) & BFL_AWAKE)) continue;
+            if (!overlap_edge(key_edge(key), b)) { destroy_contact(i); continue; }
+            contact_update(i);
+        }
+    }
+
+    // ---- contact constraints in shared memory
+    // Build the velocity constraint of pool contact c in hot slot t from the CURRENT solver pose of its body
+    // (b2ContactSolver ctor + InitializeVelocityConstraints). cB/aB are passed in.
+    __device__ __forceinline__ void contact_init_velocity(int t, int c, V2 cB, float aB, float mB, float iB, float dtRatio, bool warm) {
+        int key = Ci(CF_KEY, c);
+        int b = key_body(key);
+        int flags = key_flags(key);
+        int type = (flags >> CK_TYPE_SHIFT) & 3, count = (flags >> CK_COUNT_SHIFT) & 3;
+        float radiusB = (Bi(BF_FLAGS, b) & BFL_CIRCLE) ? B(BF_HX, b) : RB_POLY_RADIUS;
+        const float radiusA = RB_POLY_RADIUS;
+        Rot qB = rot_set(aB);
+        V2 pB = cB;                                  // xfB.p = cB - R(aB) * 0
+        V2 ln = mk(C(CF_LNX, c), C(CF_LNY, c)), lp = mk(C(CF_LPX, c), C(CF_LPY, c));
+        V2 l0 = mk(C(CF_P0X, c), C(CF_P0Y, c)), l1 = mk(C(CF_P1X, c), C(CF_P1Y, c));
+        V2 normal, wp0, wp1 = mk(0.0f, 0.0f);
+        if (type == MT_CIRCLES) {
+            normal = mk(1.0f, 0.0f);
+            V2 pointA = lp, pointB = xmul(pB, qB, l0);
+            V2 d = pointA - pointB;
+            if (dot(d, d) > RB_EPS * RB_EPS) { normal = pointB - pointA; normalize(normal); }
+            V2 cA = pointA + radiusA * normal, cBp = pointB - radiusB * normal;
+            wp0 = 0.5f * (cA + cBp);
+        } else if (type == MT_FACE_A) {
+            normal = ln;
+            V2 planePoint = lp;
+            V2 clip = xmul(pB, qB, l0);
+            V2 cA = clip + (radiusA - dot(clip - planePoint, normal)) * normal, cBp = clip - radiusB * normal;
+            wp0 = 0.5f * (cA + cBp);
+            if (count > 1) {
+                clip = xmul(pB, qB, l1);
+                cA = clip + (radiusA - dot(clip - planePoint, normal)) * normal; cBp = clip - radiusB * normal;
+                wp1 = 0.5f * (cA + cBp);
+            }
+        } else {
+            V2 nrm = rmul(qB, ln);
+            V2 planePoint = xmul(pB, qB, lp);
+            V2 clip = l0;
+            V2 cBp = clip + (radiusB - dot(clip - planePoint, nrm)) * nrm, cA = clip - radiusA * nrm;
+            wp0 = 0.5f * (cA + cBp);
+            if (count > 1) {
+                clip = l1;
+                cBp = clip + (radiusB - dot(clip - planePoint, nrm)) * nrm; cA = clip - radiusA * nrm;
+                wp1 = 0.5f * (cA + cBp);
+            }
+            normal = -nrm;
+        }
+        V2 tangent = cross_vs(normal, 1.0f);
+        V2 r0 = wp0 - cB, r1 = wp1 - cB;
+        float rn0 = cross(r0, normal), rt0 = cross(r0, tangent);
+        float kN0 = mB + iB * rn0 * rn0, kT0 = mB + iB * rt0 * rt0;
+        HC(HC_NX, t) = normal.x; HC(HC_NY, t) = normal.y;
+        HC(HC_R0X, t) = r0.x; HC(HC_R0Y, t) = r0.y;
+        HC(HC_NM0, t) = kN0 > 0.0f ? 1.0f / kN0 : 0.0f;
+        HC(HC_TM0, t) = kT0 > 0.0f ? 1.0f / kT0 : 0.0f;
+        HC(HC_NI0, t) = warm ? dtRatio * C(CF_P0N, c) : 0.0f;
+        HC(HC_TI0, t) = warm ? dtRatio * C(CF_P0T, c) : 0.0f;
+        int vcount = count;
+        if (count > 1) {
+            float rn1 = cross(r1, normal), rt1 = cross(r1, tangent);
+            float kN1 = mB + iB * rn1 * rn1, kT1 = mB + iB * rt1 * rt1;
+            HC(HC_R1X, t) = r1.x; HC(HC_R1Y, t) = r1.y;
+            HC(HC_NM1, t) = kN1 > 0.0f ? 1.0f / kN1 : 0.0f;
+            HC(HC_TM1, t) = kT1 > 0.0f ? 1.0f / kT1 : 0.0f;
+            HC(HC_NI1, t) = warm ? dtRatio * C(CF_P1N, c) : 0.0f;
+            HC(HC_TI1, t) = warm ? dtRatio * C(CF_P1T, c) : 0.0f;
+            float k11 = mB + iB * rn0 * rn0, k22 = mB + iB * rn1 * rn1, k12 = mB + iB * rn0 * rn1;
+            if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+                HC(HC_K11, t) = k11; HC(HC_K12, t) = k12; HC(HC_K22, t) = k22;
+                float det = k11 * k22 - k12 * k12;
+                if (det != 0.0f) det = 1.0f / det;
+                HC(HC_IXX, t) = det * k22; HC(HC_IXY, t) = -det * k12; HC(HC_IYY, t) = det * k11;
+            } else vcount = 1;
+        }
+        HC(HC_META, t) = __int_as_float(b | (vcount << 8) | (c << 16));
+    }
+
+    // one sequential-impulse pass over hot contact slot t (b2ContactSolver::SolveVelocityConstraints)
+    __device__ __forceinline__ void contact_solve_velocity(int t) {
+        int meta = HCi(HC_META, t);
+        int b = meta & 0xff, count = (meta >> 8) & 3;
+        float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+        V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
+        V2 normal = mk(HC(HC_NX, t), HC(HC_NY, t)), tangent = cross_vs(normal, 1.0f);
+        const float friction = k->friction;
+        V2 r0 = mk(HC(HC_R0X, t), HC(HC_R0Y, t));
+        {   // friction, point 0
+            V2 dv = vB + cross_sv(wB, r0);
+            float vt = dot(dv, tangent);
+            float lambda = HC(HC_TM0, t) * (-vt);
+            float ti = HC(HC_TI0, t);
+            float maxF = friction * HC(HC_NI0, t);
+            float ni = clampf(ti + lambda, -maxF, maxF);
+            lambda = ni - ti; HC(HC_TI0, t) = ni;
+            V2 P = lambda * tangent;
+            vB = vB + mB * P; wB += iB * cross(r0, P);
+        }
+        if (count == 1) {
+            V2 dv = vB + cross_sv(wB, r0);
+            float vn = dot(dv, normal);
+            float lambda = -HC(HC_NM0, t) * vn;
+            float ni0 = HC(HC_NI0, t);
+            float ni = max2(ni0 + lambda, 0.0f);
+            lambda = ni - ni0; HC(HC_NI0, t) = ni;
+            V2 P = lambda * normal;
+            vB = vB + mB * P; wB += iB * cross(r0, P);
+        } else {
+            V2 r1 = mk(HC(HC_R1X, t), HC(HC_R1Y, t));
+            {   // friction, point 1
+                V2 dv = vB + cross_sv(wB, r1);
+                float vt = dot(dv, tangent);
+                float lambda = HC(HC_TM1, t) * (-vt);
+                float ti = HC(HC_TI1, t);
+                float maxF = friction * HC(HC_NI1, t);
+                float ni = clampf(ti + lambda, -maxF, maxF);
+                lambda = ni - ti; HC(HC_TI1, t) = ni;
+                V2 P = lambda * tangent;
+                vB = vB + mB * P; wB += iB * cross(r1, P);
+            }
+            float a1 = HC(HC_NI0, t), a2 = HC(HC_NI1, t);
+            V2 dv1 = vB + cross_sv(wB, r0), dv2 = vB + cross_sv(wB, r1);
+            float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+            float k11 = HC(HC_K11, t), k12 = HC(HC_K12, t), k22 = HC(HC_K22, t);
+            float bx = vn1 - (k11 * a1 + k12 * a2), by = vn2 - (k12 * a1 + k22 * a2);
+            float x1, x2; bool solved = false;
+            x1 = -(HC(HC_IXX, t) * bx + HC(HC_IXY, t) * by); x2 = -(HC(HC_IXY, t) * bx + HC(HC_IYY, t) * by);
+            if (x1 >= 0.0f && x2 >= 0.0f) solved = true;
+            if (!solved) { x1 = -HC(HC_NM0, t) * bx; x2 = 0.0f; vn2 = k12 * x1 + by; if (x1 >= 0.0f && vn2 >= 0.0f) solved = true; }
+            if (!solved) { x1 = 0.0f; x2 = -HC(HC_NM1, t) * by; vn1 = k12 * x2 + bx; if (x2 >= 0.0f && vn1 >= 0.0f) solved = true; }
+            if (!solved) { x1 = 0.0f; x2 = 0.0f; if (bx >= 0.0f && by >= 0.0f) solved = true; }
+            if (solved) {
+                float d1 = x1 - a1, d2 = x2 - a2;
+                V2 P1 = d1 * normal, P2 = d2 * normal;
+                vB = vB + mB * (P1 + P2);
+                wB += iB * (cross(r0, P1) + cross(r1, P2));
+                HC(HC_NI0, t) = x1; HC(HC_NI1, t) = x2;
+            }
+        }
+        HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+    }
+
+    __device__ __forceinline__ void count_contact_solves(int nt, int vit) {
+        int n1 = 0, n2 = 0;
+        for (int t = 0; t < nt; ++t) { if (((HCi(HC_META, t) >> 8) & 3) == 1) ++n1; else ++n2; }
+        cnt.c[REM2D_CNT_P1_VSOLVES] += (unsigned)(n1 * vit);
+        cnt.c[REM2D_CNT_M2_VSOLVES] += (unsigned)(n2 * vit);
+    }
+    // position manifold of point j of hot (position overlay) slot t; returns separation
+    __device__ __forceinline__ float psm(int t, int type, int j, V2 cB, float aB, V2& normal, V2& point) {
+        Rot qB = rot_set(aB);
+        V2 lp = mk(HC(PC_LPX, t), HC(PC_LPY, t));
+        V2 lpt = j == 0 ? mk(HC(PC_P0X, t), HC(PC_P0Y, t)) : mk(HC(PC_P1X, t), HC(PC_P1Y, t));
+        const float radiusA = RB_POLY_RADIUS;
+        float radiusB = HC(PC_RADB, t);
+        if (type == MT_CIRCLES) {
+            V2 pointA = lp, pointB = xmul(cB, qB, mk(HC(PC_P0X, t), HC(PC_P0Y, t)));
+            normal = pointB - pointA;
+            normalize(normal);
+            point = 0.5f * (pointA + pointB);
+            return dot(pointB - pointA, normal) - radiusA - radiusB;
+        } else if (type == MT_FACE_A) {
+            normal = mk(HC(PC_LNX, t), HC(PC_LNY, t));
+            V2 clip = xmul(cB, qB, lpt);
+            point = clip;
+            return dot(clip - lp, normal) - radiusA - radiusB;
+        } else {
+            V2 nrm = rmul(qB, mk(HC(PC_LNX, t), HC(PC_LNY, t)));
+            V2 planePoint = xmul(cB, qB, lp);
+            V2 clip = lpt;
+            float sep = dot(clip - planePoint, nrm) - radiusA - radiusB;
+            point = clip;
+            normal = -nrm;
+            return sep;
+        }
+    }
+    // one pass of Solve(TOI)PositionConstraints over hot slot t; returns the min separation seen
+    __device__ __forceinline__ float contact_solve_position(int t, float baumgarte, float minSeparation) {
+        int meta = HCi(PC_META, t);
+        int b = meta & 0xff, count = (meta >> 8) & 3, type = (meta >> 10) & 3;
+        float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+        V2 cB = mk(HB(HB_VX, b), HB(HB_VY, b)); float aB = HB(HB_W, b);     // position overlay: c, a
+        for (int j = 0; j < count; ++j) {
+            cnt.c[REM2D_CNT_POINT_PSOLVES]++;
+            V2 normal, point;
+            float separation = psm(t, type, j, cB, aB, normal, point);
+            V2 rB = point - cB;
+            minSeparation = min2(minSeparation, separation);
+            float Cc = clampf(baumgarte * (separation + RB_LINEAR_SLOP), -RB_MAX_LIN_CORR, 0.0f);
+            float rnB = cross(rB, normal);
+            float K = mB + iB * rnB * rnB;
+            float impulse = K > 0.0f ? -Cc / K : 0.0f;
+            V2 P = impulse * normal;
+            cB = cB + mB * P; aB += iB * cross(rB, P);
+        }
+        HB(HB_VX, b) = cB.x; HB(HB_VY, b) = cB.y; HB(HB_W, b) = aB;
+        return minSeparation;
+    }
+    // copy the position-constraint data of pool contact c into hot slot t
+    __device__ __forceinline__ void contact_init_position(int t, int c) {
+        int key = Ci(CF_KEY, c);
+        int b = key_body(key), flags = key_flags(key);
+        int type = (flags >> CK_TYPE_SHIFT) & 3, count = (flags >> CK_COUNT_SHIFT) & 3;
+        HC(PC_META, t) = __int_as_float(b | (count << 8) | (type << 10));
+        HC(PC_LNX, t) = C(CF_LNX, c); HC(PC_LNY, t) = C(CF_LNY, c);
+        HC(PC_LPX, t) = C(CF_LPX, c); HC(PC_LPY, t) = C(CF_LPY, c);
+        HC(PC_P0X, t) = C(CF_P0X, c); HC(PC_P0Y, t) = C(CF_P0Y, c);
+        HC(PC_P1X, t) = C(CF_P1X, c); HC(PC_P1Y, t) = C(CF_P1Y, c);
+        HC(PC_RADB, t) = (Bi(BF_FLAGS, b) & BFL_CIRCLE) ? B(BF_HX, b) : RB_POLY_RADIUS;
+    }
+
+    // ---- revolute joints in shared memory (b2RevoluteJoint)
+    __device__ __forceinline__ void joint_solve_velocity(int s) {
+        int meta = HJi(HJ_META, s);
+        int a = meta & 0xff, b = (meta >> 8) & 0xff, limit = (meta >> 16) & 3;
+        float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+        V2 vA = mk(HB(HB_VX, a), HB(HB_VY, a)); float wA = HB(HB_W, a);
+        V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
+        V2 rA = mk(HJ(HJ_RAX, s), HJ(HJ_RAY, s)), rB = mk(HJ(HJ_RBX, s), HJ(HJ_RBY, s));
+        {   // motor
+            float Cdot = wB - wA - HJ(HJ_MSPEED, s);
+            float impulse = -HJ(HJ_MMASS, s) * Cdot;
+            float oldImpulse = HJ(HJ_MIMP, s);
+            float maxImpulse = HJ(HJ_MAXIMP, s);
+            float ni = clampf(oldImpulse + impulse, -maxImpulse, maxImpulse);
+            HJ(HJ_MIMP, s) = ni;
+            impulse = ni - oldImpulse;
+            wA -= iA * impulse; wB += iB * impulse;
+        }
+        float exx = HJ(HJ_EXX, s), eyx = HJ(HJ_EYX, s), eyy = HJ(HJ_EYY, s);
+        if (limit != 0) {
+            float ezx = HJ(HJ_EZX, s), ezy = HJ(HJ_EZY, s), ezz = HJ(HJ_EZZ, s);
+            V2 Cdot1 = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
+            float Cdot2 = wB - wA;
+            // Solve33: ex = (exx, eyx, ezx), ey = (eyx, eyy, ezy), ez = (ezx, ezy, ezz)
+            float cx = eyy * ezz - ezy * ezy, cy = ezy * ezx - eyx * ezz, cz = eyx * ezy - eyy * ezx;   // ey x ez
+            float det = exx * cx + eyx * cy + ezx * cz;
+            if (det != 0.0f) det = 1.0f / det;
+            float ix = det * (Cdot1.x * cx + Cdot1.y * cy + Cdot2 * cz);
+            // b x ez
+            float bx = Cdot1.y * ezz - Cdot2 * ezy, by = Cdot2 * ezx - Cdot1.x * ezz, bz = Cdot1.x * ezy - Cdot1.y * ezx;
+            float iy = det * (exx * bx + eyx * by + ezx * bz);
+            // ey x b
+            float ex2 = eyy * Cdot2 - ezy * Cdot1.y, ey2 = ezy * Cdot1.x - eyx * Cdot2, ez2 = eyx * Cdot1.y - eyy * Cdot1.x;
+            float iz = det * (exx * ex2 + eyx * ey2 + ezx * ez2);
+            ix = -ix; iy = -iy; iz = -iz;
+            float jz = HJ(HJ_IMPZ, s);
+            float newImpulse = jz + iz;
+            bool reduce = (limit == 1) ? (newImpulse < 0.0f) : (newImpulse > 0.0f);
+            if (reduce) {
+                V2 rhs = -Cdot1 + jz * mk(ezx, ezy);
+                float d2 = exx * eyy - eyx * eyx;
+                if (d2 != 0.0f) d2 = 1.0f / d2;
+                float rx = d2 * (eyy * rhs.x - eyx * rhs.y), ry = d2 * (exx * rhs.y - eyx * rhs.x);
+                ix = rx; iy = ry; iz = -jz;
+                HJ(HJ_IMPX, s) += rx; HJ(HJ_IMPY, s) += ry; HJ(HJ_IMPZ, s) = 0.0f;
+            } else {
+                HJ(HJ_IMPX, s) += ix; HJ(HJ_IMPY, s) += iy; HJ(HJ_IMPZ, s) = jz + iz;
+            }
+            V2 P = mk(ix, iy);
+            vA = vA - mA * P; wA -= iA * (cross(rA, P) + iz);
+            vB = vB + mB * P; wB += iB * (cross(rB, P) + iz);
+        } else {
+            V2 Cdot = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
+            V2 nb_ = -Cdot;
+            float d2 = exx * eyy - eyx * eyx;
+            if (d2 != 0.0f) d2 = 1.0f / d2;
+            V2 imp = mk(d2 * (eyy * nb_.x - eyx * nb_.y), d2 * (exx * nb_.y - eyx * nb_.x));
+            HJ(HJ_IMPX, s) += imp.x; HJ(HJ_IMPY, s) += imp.y;
+            vA = vA - mA * imp; wA -= iA * cross(rA, imp);
+            vB = vB + mB * imp; wB += iB * cross(rB, imp);
+        }
+        HB(HB_VX, a) = vA.x; HB(HB_VY, a) = vA.y; HB(HB_W, a) = wA;
+        HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+    }
+    __device__ __forceinline__ bool joint_solve_position(int s) {
+        int meta = HJi(PJ_META, s);
+        int a = meta & 0xff, b = (meta >> 8) & 0xff, limit = (meta >> 16) & 3;
+        float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+        V2 cA = mk(HB(HB_VX, a), HB(HB_VY, a)); float aA = HB(HB_W, a);
+        V2 cB = mk(HB(HB_VX, b), HB(HB_VY, b)); float aB = HB(HB_W, b);
+        float angularError = 0.0f, positionError = 0.0f;
+        if (limit != 0) {
+            float motorMass = iA + iB;
+            if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
+            float angle = aB - aA - 0.0f;
+            float limitImpulse = 0.0f;
+            if (limit == 1) {
+                float Cc = angle - HJ(PJ_LOWER, s);
+                angularError = -Cc;
+                Cc = clampf(Cc + RB_ANGULAR_SLOP, -RB_MAX_ANG_CORR, 0.0f);
+                limitImpulse = -motorMass * Cc;
+            } else {
+                float Cc = angle - HJ(PJ_UPPER, s);
+                angularError = Cc;
+                Cc = clampf(Cc - RB_ANGULAR_SLOP, 0.0f, RB_MAX_ANG_CORR);
+                limitImpulse = -motorMass * Cc;
+            }
+            aA -= iA * limitImpulse; aB += iB * limitImpulse;
+        }
+        Rot qA = rot_set(aA), qB = rot_set(aB);
+        V2 rA = rmul(qA, mk(HJ(PJ_LAAX, s), HJ(PJ_LAAY, s)) - mk(0.0f, 0.0f));
+        V2 rB = rmul(qB, mk(HJ(PJ_LABX, s), HJ(PJ_LABY, s)) - mk(0.0f, 0.0f));
+        V2 Cv = cB + rB - cA - rA;
+        positionError = len(Cv);
+        float kexx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+        float kexy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+        float keyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+        float det = kexx * keyy - kexy * kexy;
+        if (det != 0.0f) det = 1.0f / det;
+        V2 imp = -mk(det * (keyy * Cv.x - kexy * Cv.y), det * (kexx * Cv.y - kexy * Cv.x));
+        cA = cA - mA * imp; aA -= iA * cross(rA, imp);
+        cB = cB + mB * imp; aB += iB * cross(rB, imp);
+        HB(HB_VX, a) = cA.x; HB(HB_VY, a) = cA.y; HB(HB_W, a) = aA;
+        HB(HB_VX, b) = cB.x; HB(HB_VY, b) = cB.y; HB(HB_W, b) = aB;
+        return positionError <= RB_LINEAR_SLOP && angularError <= RB_ANGULAR_SLOP;
+    }
+
+    // ---- b2World::Solve for the creature's single island (+ SynchronizeFixtures + FindNewContacts)
+    __device__ void solve(float dtRatio) {
+        const float hdt = k->dt;
+        // a creature is one island (tree of joints); it is solved iff its seed body is awake. Jointed
+        // creatures are always awake here (the motor-speed setter woke them); a lone body may sleep.
+        bool anyAwake = false;
+        for (int b = 0; b < nb; ++b) anyAwake |= (Bi(BF_FLAGS, b) & BFL_AWAKE) != 0;
+        if (!anyAwake) return;
+        for (int b = 0; b < nb; ++b) {
+            set_awake(b, true);
+            float cx = B(BF_CX, b), cy = B(BF_CY, b), a = B(BF_A, b);
+            B(BF_C0X, b) = cx; B(BF_C0Y, b) = cy; B(BF_A0, b) = a;
+            V2 v = mk(B(BF_VX, b), B(BF_VY, b)); float w = B(BF_W, b);
+            float invM = B(BF_INVM, b), invI = B(BF_INVI, b);
+            V2 gravity = mk(0.0f, k->gravity_y), force = mk(0.0f, 0.0f);
+            v = v + hdt * (1.0f * gravity + invM * force);
+            w += hdt * invI * 0.0f;
+            v = (1.0f / (1.0f + hdt * 0.0f)) * v;
+            w *= 1.0f / (1.0f + hdt * 0.0f);
+            HB(HB_VX, b) = v.x; HB(HB_VY, b) = v.y; HB(HB_W, b) = w;
+            HB(HB_INVM, b) = invM; HB(HB_INVI, b) = invI;
+            cnt.c[REM2D_CNT_BODY_TICKS]++;
+        }
+        // contact constraints: touching contacts, newest first (per-body list order is what matters:
+        // contacts of different bodies only share the static terrain and commute exactly)
+        int nc = Si(S_NC), nt = 0;
+        for (int c = nc - 1; c >= 0; --c) {
+            int key = Ci(CF_KEY, c);
+            int fl = key_flags(key);
+            if (!(fl & CK_ENABLED) || !(fl & CK_TOUCHING)) continue;
+            if (nt == NT) { setSi(S_STATUS, Si(S_STATUS) | ST_HOT_OVERFLOW); break; }
+            int b = key_body(key);
+            contact_init_velocity(nt, c, mk(B(BF_CX, b), B(BF_CY, b)), B(BF_A, b), B(BF_INVM, b), B(BF_INVI, b), dtRatio, true);
+            ++nt;
+        }
+        // warm start contacts
+        for (int t = 0; t < nt; ++t) {
+            int meta = HCi(HC_META, t);
+            int b = meta & 0xff, count = (meta >> 8) & 3;
+            float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+            V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
+            V2 normal = mk(HC(HC_NX, t), HC(HC_NY, t)), tangent = cross_vs(normal, 1.0f);
+            {
+                V2 r = mk(HC(HC_R0X, t), HC(HC_R0Y, t));
+                V2 P = HC(HC_NI0, t) * normal + HC(HC_TI0, t) * tangent;
+                wB += iB * cross(r, P); vB = vB + mB * P;
+            }
+            if (count > 1) {
+                V2 r = mk(HC(HC_R1X, t), HC(HC_R1Y, t));
+                V2 P = HC(HC_NI1, t) * normal + HC(HC_TI1, t) * tangent;
+                wB += iB * cross(r, P); vB = vB + mB * P;
+            }
+            HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+        }
+        // joints: InitVelocityConstraints in island order (slot s = s-th joint of the island)
+        for (int s = 0; s < nj; ++s) {
+            int jm = Ji(JF_META, s);
+            int j = (jm >> 8) & 0xff;                  // joint index solved s-th
+            int a = Ji(JF_META, j) & 0xff, b = j + 1;
+            float aA = B(BF_A, a), aB = B(BF_A, b);
+            float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+            Rot qA = rot_set(aA), qB = rot_set(aB);
+            V2 rA = rmul(qA, mk(J(JF_LAAX, j), J(JF_LAAY, j)) - mk(0.0f, 0.0f));
+            V2 rB = rmul(qB, mk(J(JF_LABX, j), J(JF_LABY, j)) - mk(0.0f, 0.0f));
+            float exx = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+            float eyx = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+            float ezx = -rA.y * iA - rB.y * iB;
+            float eyy = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+            float ezy = rA.x * iA + rB.x * iB;
+            float ezz = iA + iB;
+            float motorMass = iA + iB;
+            if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
+            float impx = J(JF_IMPX, j), impy = J(JF_IMPY, j), impz = J(JF_IMPZ, j), mimp = J(JF_MIMP, j);
+            int limit = Ji(JF_LIMIT, j);
+            float jointAngle = aB - aA - 0.0f;
+            float lower = J(JF_LOWER, j), upper = J(JF_UPPER, j);
+            if (jointAngle <= lower) { if (limit != 1) impz = 0.0f; limit = 1; }
+            else if (jointAngle >= upper) { if (limit != 2) impz = 0.0f; limit = 2; }
+            else { limit = 0; impz = 0.0f; }
+            setJi(JF_LIMIT, j, limit);
+            impx *= dtRatio; impy *= dtRatio; impz *= dtRatio; mimp *= dtRatio;
+            V2 vA = mk(HB(HB_VX, a), HB(HB_VY, a)); float wA = HB(HB_W, a);
+            V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
+            V2 P = mk(impx, impy);
+            vA = vA - mA * P; wA -= iA * (cross(rA, P) + mimp + impz);
+            vB = vB + mB * P; wB += iB * (cross(rB, P) + mimp + impz);
+            HB(HB_VX, a) = vA.x; HB(HB_VY, a) = vA.y; HB(HB_W, a) = wA;
+            HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+            HJ(HJ_META, s) = __int_as_float(a | (b << 8) | (limit << 16) | (j << 24));
+            HJ(HJ_RAX, s) = rA.x; HJ(HJ_RAY, s) = rA.y; HJ(HJ_RBX, s) = rB.x; HJ(HJ_RBY, s) = rB.y;
+            HJ(HJ_EXX, s) = exx; HJ(HJ_EYX, s) = eyx; HJ(HJ_EZX, s) = ezx; HJ(HJ_EYY, s) = eyy; HJ(HJ_EZY, s) = ezy; HJ(HJ_EZZ, s) = ezz;
+            HJ(HJ_MMASS, s) = motorMass;
+            HJ(HJ_IMPX, s) = impx; HJ(HJ_IMPY, s) = impy; HJ(HJ_IMPZ, s) = impz; HJ(HJ_MIMP, s) = mimp;
+            HJ(HJ_MSPEED, s) = J(JF_MSPEED, j);
+            HJ(HJ_MAXIMP, s) = hdt * J(JF_MAXT, j);
+        }
+        // ---------------- velocity iterations: the hot loop (everything in shared memory)
+        // NB: equal limits (|upper-lower| < 2*angularSlop) do not occur: limits are -+pi/2 (module_utility.py:28-29)
+        const int vit = k->vel_iters;
+        for (int it = 0; it < vit; ++it) {
+            for (int s = 0; s < nj; ++s) joint_solve_velocity(s);
+            for (int t = 0; t < nt; ++t) contact_solve_velocity(t);
+        }
+        cnt.c[REM2D_CNT_JOINT_VSOLVES] += (unsigned)(vit * nj);
+        count_contact_solves(nt, vit);
+        // store impulses
+        for (int t = 0; t < nt; ++t) {
+            int meta = HCi(HC_META, t);
+            int c = (meta >> 16) & 0xffff, count = (meta >> 8) & 3;
+            C(CF_P0N, c) = HC(HC_NI0, t); C(CF_P0T, c) = HC(HC_TI0, t);
+            if (count > 1) { C(CF_P1N, c) = HC(HC_NI1, t); C(CF_P1T, c) = HC(HC_TI1, t); }
+        }
+        for (int s = 0; s < nj; ++s) {
+            int j = (HJi(HJ_META, s) >> 24) & 0xff;
+            J(JF_IMPX, j) = HJ(HJ_IMPX, s); J(JF_IMPY, j) = HJ(HJ_IMPY, s); J(JF_IMPZ, j) = HJ(HJ_IMPZ, s);
+            J(JF_MIMP, j) = HJ(HJ_MIMP, s);
+        }
+        // integrate positions; velocities go back to the cold block, the hot body slots become (c, a)
+        for (int b = 0; b < nb; ++b) {
+            V2 c = mk(B(BF_CX, b), B(BF_CY, b)); float a = B(BF_A, b);
+            V2 v = mk(HB(HB_VX, b), HB(HB_VY, b)); float w = HB(HB_W, b);
+            V2 translation = hdt * v;
+            if (dot(translation, translation) > RB_MAX_TRANS * RB_MAX_TRANS) {
+                float ratio = RB_MAX_TRANS / len(translation);
+                v = ratio * v;
+            }
+            float rotation = hdt * w;
+            if (rotation * rotation > RB_MAX_ROT * RB_MAX_ROT) {
+                float ratio = RB_MAX_ROT / abs2(rotation);
+                w *= ratio;
+            }
+            c = c + hdt * v; a += hdt * w;
+            B(BF_VX, b) = v.x; B(BF_VY, b) = v.y; B(BF_W, b) = w;
+            HB(HB_VX, b) = c.x; HB(HB_VY, b) = c.y; HB(HB_W, b) = a;
+        }
+        // position constraints: overlay the hot joint / contact slots
+        for (int s = 0; s < nj; ++s) {
+            int meta = HJi(HJ_META, s);
+            int j = (meta >> 24) & 0xff;
+            HJ(PJ_LAAX, s) = J(JF_LAAX, j); HJ(PJ_LAAY, s) = J(JF_LAAY, j);
+            HJ(PJ_LABX, s) = J(JF_LABX, j); HJ(PJ_LABY, s) = J(JF_LABY, j);
+            HJ(PJ_LOWER, s) = J(JF_LOWER, j); HJ(PJ_UPPER, s) = J(JF_UPPER, j);
+        }
+        for (int t = 0; t < nt; ++t) {
+            int c = (HCi(HC_META, t) >> 16) & 0xffff;
+            contact_init_position(t, c);
+        }
+        bool positionSolved = false;
+        const int pit = k->pos_iters;
+        for (int it = 0; it < pit; ++it) {
+            float minSep = 0.0f;
+            for (int t = 0; t < nt; ++t) minSep = contact_solve_position(t, RB_BAUMGARTE, minSep);
+            bool contactsOkay = minSep >= -3.0f * RB_LINEAR_SLOP;
+            bool jointsOkay = true;
+            for (int s = 0; s < nj; ++s) { bool ok = joint_solve_position(s); jointsOkay = jointsOkay && ok; }
+            cnt.c[REM2D_CNT_JOINT_PSOLVES] += (unsigned)nj;
+            if (contactsOkay && jointsOkay) { positionSolved = true; break; }
+        }
+        // copy back, synchronize transforms, sleep management
+        float minSleepTime = RB_MAXF;
+        for (int b = 0; b < nb; ++b) {
+            B(BF_CX, b) = HB(HB_VX, b); B(BF_CY, b) = HB(HB_VY, b); B(BF_A, b) = HB(HB_W, b);
+            sync_transform(b);
+            if (k->allow_sleep) {
+                float w = B(BF_W, b); V2 v = mk(B(BF_VX, b), B(BF_VY, b));
+                if (w * w > RB_ANG_SLEEP_TOL * RB_ANG_SLEEP_TOL || dot(v, v) > RB_LIN_SLEEP_TOL * RB_LIN_SLEEP_TOL) {
+                    B(BF_SLEEP, b) = 0.0f; minSleepTime = 0.0f;
+                } else {
+                    float st = B(BF_SLEEP, b) + hdt;
+                    B(BF_SLEEP, b) = st; minSleepTime = min2(minSleepTime, st);
+                }
+            }
+        }
+        if (k->allow_sleep && minSleepTime >= RB_TIME_TO_SLEEP && positionSolved)
+            for (int b = 0; b < nb; ++b) set_awake(b, false);
+        for (int b = nb - 1; b >= 0; --b) synchronize_fixtures(b);
+        find_new_contacts();
+    }
+
+    // ---- continuous collision: b2TimeOfImpact / b2Distance with proxy A = terrain edge (identity frame)
+    struct Sweep { V2 c0, c; float a0, a, alpha0; };
+    struct Prox { V2 v[4]; int count; float radius; };
+    struct SimplexCache { float metric; int count; int ia[3], ib[3]; };
+    struct SV { V2 wA, wB, w; float a; int ia, ib; };
+
+    __device__ __forceinline__ void sweep_xf(const Sweep& s, float beta, V2& p, Rot& q) {
+        p = (1.0f - beta) * s.c0 + beta * s.c;
+        float angle = (1.0f - beta) * s.a0 + beta * s.a;
+        q = rot_set(angle);
+        p = p - rmul(q, mk(0.0f, 0.0f));
+    }
+    __device__ __forceinline__ int support(const V2* v, int count, V2 d) {
+        int best = 0; float bestValue = dot(v[0], d);
+        for (int i = 1; i < count; ++i) { float value = dot(v[i], d); if (value > bestValue) { best = i; bestValue = value; } }
+        return best;
+    }
+    __device__ __forceinline__ float metric(const SV* s, int count) {
+        if (count == 2) return len(s[0].w - s[1].w);
+        if (count == 3) return cross(s[1].w - s[0].w, s[2].w - s[0].w);
+        return 0.0f;
+    }
+    __device__ float gjk(SimplexCache& cache, const V2* ev, const Prox& pb, V2 pB, Rot qB) {
+        SV s[3]; int count = cache.count;
+        for (int i = 0; i < count; ++i) {
+            s[i].ia = cache.ia[i]; s[i].ib = cache.ib[i];
+            s[i].wA = ev[s[i].ia];
+            s[i].wB = xmul(pB, qB, pb.v[s[i].ib]);
+            s[i].w = s[i].wB - s[i].wA; s[i].a = 0.0f;
+        }
+        if (count > 1) {
+            float m1 = cache.metric, m2 = metric(s, count);
+            if (m2 < 0.5f * m1 || 2.0f * m1 < m2 || m2 < RB_EPS) count = 0;
+        }
+        if (count == 0) {
+            s[0].ia = 0; s[0].ib = 0; s[0].wA = ev[0]; s[0].wB = xmul(pB, qB, pb.v[0]);
+            s[0].w = s[0].wB - s[0].wA; s[0].a = 1.0f; count = 1;
+        }
+        int saveA[3], saveB[3], saveCount = 0, iter = 0;
+        while (iter < 20) {
+            saveCount = count;
+            for (int i = 0; i < saveCount; ++i) { saveA[i] = s[i].ia; saveB[i] = s[i].ib; }
+            if (count == 2) {
+                V2 w1 = s[0].w, w2 = s[1].w, e12 = w2 - w1;
+                float d12_2 = -dot(w1, e12);
+                if (d12_2 <= 0.0f) { s[0].a = 1.0f; count = 1; }
+                else {
+                    float d12_1 = dot(w2, e12);
+                    if (d12_1 <= 0.0f) { s[1].a = 1.0f; count = 1; s[0] = s[1]; }
+                    else { float inv = 1.0f / (d12_1 + d12_2); s[0].a = d12_1 * inv; s[1].a = d12_2 * inv; count = 2; }
+                }
+            } else if (count == 3) {
+                V2 w1 = s[0].w, w2 = s[1].w, w3 = s[2].w;
+                V2 e12 = w2 - w1; float w1e12 = dot(w1, e12), w2e12 = dot(w2, e12); float d12_1 = w2e12, d12_2 = -w1e12;
+                V2 e13 = w3 - w1; float w1e13 = dot(w1, e13), w3e13 = dot(w3, e13); float d13_1 = w3e13, d13_2 = -w1e13;
+                V2 e23 = w3 - w2; float w2e23 = dot(w2, e23), w3e23 = dot(w3, e23); float d23_1 = w3e23, d23_2 = -w2e23;
+                float n123 = cross(e12, e13);
+                float d123_1 = n123 * cross(w2, w3), d123_2 = n123 * cross(w3, w1), d123_3 = n123 * cross(w1, w2);
+                if (d12_2 <= 0.0f && d13_2 <= 0.0f) { s[0].a = 1.0f; count = 1; }
+                else if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) { float inv = 1.0f / (d12_1 + d12_2); s[0].a = d12_1 * inv; s[1].a = d12_2 * inv; count = 2; }
+                else if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) { float inv = 1.0f / (d13_1 + d13_2); s[0].a = d13_1 * inv; s[2].a = d13_2 * inv; count = 2; s[1] = s[2]; }
+                else if (d12_1 <= 0.0f && d23_2 <= 0.0f) { s[1].a = 1.0f; count = 1; s[0] = s[1]; }
+                else if (d13_1 <= 0.0f && d23_1 <= 0.0f) { s[2].a = 1.0f; count = 1; s[0] = s[2]; }
+                else if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) { float inv = 1.0f / (d23_1 + d23_2); s[1].a = d23_1 * inv; s[2].a = d23_2 * inv; count = 2; s[0] = s[2]; }
+                else { float inv = 1.0f / (d123_1 + d123_2 + d123_3); s[0].a = d123_1 * inv; s[1].a = d123_2 * inv; s[2].a = d123_3 * inv; count = 3; }
+            }
+            if (count == 3) break;
+            V2 d;
+            if (count == 1) d = -s[0].w;
+            else {
+                V2 e12 = s[1].w - s[0].w;
+                float sgn = cross(e12, -s[0].w);
+                d = sgn > 0.0f ? cross_sv(1.0f, e12) : cross_vs(e12, 1.0f);
+            }
+            if (dot(d, d) < RB_EPS * RB_EPS) break;
+            SV& vtx = s[count];
+            vtx.ia = support(ev, 2, -d);
+            vtx.wA = ev[vtx.ia];
+            vtx.ib = support(pb.v, pb.count, rmulT(qB, d));
+            vtx.wB = xmul(pB, qB, pb.v[vtx.ib]);
+            vtx.w = vtx.wB - vtx.wA;
+            ++iter;
+            cnt.c[REM2D_CNT_GJK_ITERS]++;
+            bool dup = false;
+            for (int i = 0; i < saveCount; ++i) if (vtx.ia == saveA[i] && vtx.ib == saveB[i]) { dup = true; break; }
+            if (dup) break;
+            ++count;
+        }
+        V2 a, b;
+        if (count == 1) { a = s[0].wA; b = s[0].wB; }
+        else if (count == 2) { a = s[0].a * s[0].wA + s[1].a * s[1].wA; b = s[0].a * s[0].wB + s[1].a * s[1].wB; }
+        else { a = s[0].a * s[0].wA + s[1].a * s[1].wA + s[2].a * s[2].wA; b = a; }
+        float distance = len(a - b);
+        cache.metric = metric(s, count);
+        cache.count = count;
+        for (int i = 0; i < count; ++i) { cache.ia[i] = s[i].ia; cache.ib[i] = s[i].ib; }
+        return distance;
+    }
+
+    struct SepFn { int type; V2 localPoint, axis; };
+    __device__ __forceinline__ float sep_find_min(const SepFn& f, const V2* ev, const Prox& pb, const Sweep& sw, int& ia, int& ib, float t) {
+        V2 pB; Rot qB; sweep_xf(sw, t, pB, qB);
+        if (f.type == 0) {
+            ia = support(ev, 2, f.axis);
+            ib = support(pb.v, pb.count, rmulT(qB, -f.axis));
+            V2 pointA = ev[ia], pointB = xmul(pB, qB, pb.v[ib]);
+            return dot(pointB - pointA, f.axis);
+        } else if (f.type == 1) {
+            V2 normal = f.axis, pointA = f.localPoint;
+            ia = -1;
+            ib = support(pb.v, pb.count, rmulT(qB, -normal));
+            V2 pointB = xmul(pB, qB, pb.v[ib]);
+            return dot(pointB - pointA, normal);
+        } else {
+            V2 normal = rmul(qB, f.axis), pointB = xmul(pB, qB, f.localPoint);
+            ib = -1;
+            ia = support(ev, 2, -normal);
+            V2 pointA = ev[ia];
+            return dot(pointA - pointB, normal);
+        }
+    }
+    __device__ __forceinline__ float sep_eval(const SepFn& f, const V2* ev, const Prox& pb, const Sweep& sw, int ia, int ib, float t) {
+        V2 pB; Rot qB; sweep_xf(sw, t, pB, qB);
+        if (f.type == 0) { V2 pointA = ev[ia], pointB = xmul(pB, qB, pb.v[ib]); return dot(pointB - pointA, f.axis); }
+        else if (f.type == 1) { V2 pointB = xmul(pB, qB, pb.v[ib]); return dot(pointB - f.localPoint, f.axis); }
+        else { V2 normal = rmul(qB, f.axis), pointB = xmul(pB, qB, f.localPoint); V2 pointA = ev[ia]; return dot(pointA - pointB, normal); }
+    }
+    // returns true iff the TOI state is "touching"; t receives output.t
+    __device__ bool time_of_impact(const V2* ev, const Prox& pb, Sweep sw, float& tOut) {
+        cnt.c[REM2D_CNT_TOI_CALLS]++;
+        const float tMax = 1.0f;
+        tOut = tMax;
+        {   // b2Sweep::Normalize
+            float twoPi = 2.0f * RB_PI;
+            float d = twoPi * floorf(sw.a0 / twoPi);
+            sw.a0 -= d; sw.a -= d;
+        }
+        float totalRadius = RB_POLY_RADIUS + pb.radius;
+        float target = max2(RB_LINEAR_SLOP, totalRadius - 3.0f * RB_LINEAR_SLOP);
+        float tolerance = 0.25f * RB_LINEAR_SLOP;
+        float t1 = 0.0f;
+        int iter = 0;
+        SimplexCache cache; cache.count = 0; cache.metric = 0.0f;
+        bool touching = false;
+        for (;;) {
+            V2 pB; Rot qB; sweep_xf(sw, t1, pB, qB);
+            float distance = gjk(cache, ev, pb, pB, qB);
+            if (distance <= 0.0f) { tOut = 0.0f; break; }                         // overlapped
+            if (distance < target + tolerance) { touching = true; tOut = t1; break; }
+            SepFn f;
+            if (cache.count == 1) {
+                f.type = 0;
+                V2 pointA = ev[cache.ia[0]], pointB = xmul(pB, qB, pb.v[cache.ib[0]]);
+                f.axis = pointB - pointA; normalize(f.axis); f.localPoint = mk(0.0f, 0.0f);
+            } else if (cache.ia[0] == cache.ia[1]) {
+                f.type = 2;
+                V2 b1 = pb.v[cache.ib[0]], b2 = pb.v[cache.ib[1]];
+                f.axis = cross_vs(b2 - b1, 1.0f); normalize(f.axis);
+                V2 normal = rmul(qB, f.axis);
+                f.localPoint = 0.5f * (b1 + b2);
+                V2 pointB = xmul(pB, qB, f.localPoint), pointA = ev[cache.ia[0]];
+                float s = dot(pointA - pointB, normal);
+                if (s < 0.0f) f.axis = -f.axis;
+            } else {
+                f.type = 1;
+                V2 a1 = ev[cache.ia[0]], a2 = ev[cache.ia[1]];
+                f.axis = cross_vs(a2 - a1, 1.0f); normalize(f.axis);
+                V2 normal = f.axis;
+                f.localPoint = 0.5f * (a1 + a2);
+                V2 pointA = f.localPoint, pointB = xmul(pB, qB, pb.v[cache.ib[0]]);
+                float s = dot(pointB - pointA, normal);
+                if (s < 0.0f) f.axis = -f.axis;
+            }
+            bool done = false;
+            float t2 = tMax;
+            int pushBackIter = 0;
+            for (;;) {
+                int ia, ib;
+                float s2 = sep_find_min(f, ev, pb, sw, ia, ib, t2);
+                if (s2 > target + tolerance) { tOut = tMax; done = true; break; }                 // separated
+                if (s2 > target - tolerance) { t1 = t2; break; }
+                float s1 = sep_eval(f, ev, pb, sw, ia, ib, t1);
+                if (s1 < target - tolerance) { tOut = t1; done = true; break; }                   // failed
+                if (s1 <= target + tolerance) { touching = true; tOut = t1; done = true; break; }
+                int rootIter = 0;
+                float a1 = t1, a2 = t2;
+                for (;;) {
+                    float t;
+                    if (rootIter & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
+                    else t = 0.5f * (a1 + a2);
+                    ++rootIter;
+                    cnt.c[REM2D_CNT_TOI_ROOT_ITERS]++;
+                    float s = sep_eval(f, ev, pb, sw, ia, ib, t);
+                    if (abs2(s - target) < tolerance) { t2 = t; break; }
+                    if (s > target) { a1 = t; s1 = s; } else { a2 = t; s2 = s; }
+                    if (rootIter == 50) break;
+                }
+                ++pushBackIter;
+                if (pushBackIter == RB_MAX_POLY_VERTS) break;
+            }
+            ++iter;
+            if (done) break;
+            if (iter == 20) { tOut = t1; break; }                                                  // failed
+        }
+        return touching;
+    }
+
+    __device__ __forceinline__ void body_advance(int b, float alpha) {
+        float alpha0 = B(BF_ALPHA0, b);
+        float beta = (alpha - alpha0) / (1.0f - alpha0);
+        V2 c0 = mk(B(BF_C0X, b), B(BF_C0Y, b)), c = mk(B(BF_CX, b), B(BF_CY, b));
+        float a0 = B(BF_A0, b), a = B(BF_A, b);
+        c0 = c0 + beta * (c - c0);
+        a0 += beta * (a - a0);
+        B(BF_C0X, b) = c0.x; B(BF_C0Y, b) = c0.y; B(BF_A0, b) = a0; B(BF_ALPHA0, b) = alpha;
+        B(BF_CX, b) = c0.x; B(BF_CY, b) = c0.y; B(BF_A, b) = a0;
+        sync_transform(b);
+    }
+    __device__ __forceinline__ void set_edge_alpha(int e, float alpha) {
+        EA(e) = alpha;
+        int n = Si(S_NADV);
+        if (n < 8) setSi(S_ADV0 + n, e);
+        setSi(S_NADV, n + 1);
+    }
+
+    // b2World::SolveTOI
+    __device__ void solve_toi() {
+        const float dt = k->dt;
+        for (int b = 0; b < nb; ++b) { setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) & ~BFL_ISLAND); B(BF_ALPHA0, b) = 0.0f; }
+        {   // alpha0 of the static edge bodies: clear what the previous step dirtied
+            int n = Si(S_NADV);
+            if (n > 8) { for (int e = 0; e < RB_MAX_EDGES; ++e) EA(e) = 0.0f; }
+            else for (int i = 0; i < n; ++i) EA(Si(S_ADV0 + i)) = 0.0f;
+            setSi(S_NADV, 0);
+        }
+        int nc = Si(S_NC);
+        for (int c = 0; c < nc; ++c) {
+            int key = Ci(CF_KEY, c);
+            key &= ~((CK_TOIFLAG | CK_ISLAND) << 16);
+            key &= 0x00ffffff;                                    // toiCount = 0
+            setCi(CF_KEY, c, key);
+            C(CF_TOI, c) = 1.0f;
+        }
+        for (;;) {
+            nc = Si(S_NC);
+            int minContact = -1; float minAlpha = 1.0f;
+            for (int c = nc - 1; c >= 0; --c) {
+                int key = Ci(CF_KEY, c);
+                int fl = key_flags(key);
+                if (!(fl & CK_ENABLED)) continue;
+                if (key_toicount(key) > RB_MAX_SUBSTEPS) continue;
+                float alpha = 1.0f;
+                if (fl & CK_TOIFLAG) alpha = C(CF_TOI, c);
+                else {
+                    int b = key_body(key), e = key_edge(key);
+                    if (!(Bi(BF_FLAGS, b) & BFL_AWAKE)) continue;
+                    float aA0 = EA(e), aB0 = B(BF_ALPHA0, b);
+                    float alpha0 = aA0;
+                    Sweep sw;
+                    sw.c0 = mk(B(BF_C0X, b), B(BF_C0Y, b)); sw.c = mk(B(BF_CX, b), B(BF_CY, b));
+                    sw.a0 = B(BF_A0, b); sw.a = B(BF_A, b); sw.alpha0 = aB0;
+                    if (aA0 < aB0) { alpha0 = aB0; set_edge_alpha(e, alpha0); }
+                    else if (aB0 < aA0) {
+                        alpha0 = aA0;
+                        float beta = (alpha0 - sw.alpha0) / (1.0f - sw.alpha0);
+                        sw.c0 = sw.c0 + beta * (sw.c - sw.c0);
+                        sw.a0 += beta * (sw.a - sw.a0);
+                        sw.alpha0 = alpha0;
+                        B(BF_C0X, b) = sw.c0.x; B(BF_C0Y, b) = sw.c0.y; B(BF_A0, b) = sw.a0; B(BF_ALPHA0, b) = alpha0;
+                    }
+                    V2 ev[2] = { mk(__ldg(&ter->v1x[e]), __ldg(&ter->v1y[e])), mk(__ldg(&ter->v2x[e]), __ldg(&ter->v2y[e])) };
+                    Prox pb;
+                    float hx = B(BF_HX, b), hy = B(BF_HY, b);
+                    if (Bi(BF_FLAGS, b) & BFL_CIRCLE) { pb.count = 1; pb.radius = hx; pb.v[0] = mk(0.0f, 0.0f); pb.v[1] = pb.v[2] = pb.v[3] = pb.v[0]; }
+                    else { pb.count = 4; pb.radius = RB_POLY_RADIUS; pb.v[0] = mk(-hx, -hy); pb.v[1] = mk(hx, -hy); pb.v[2] = mk(hx, hy); pb.v[3] = mk(-hx, hy); }
+                    float t;
+                    bool touching = time_of_impact(ev, pb, sw, t);
+                    if (touching) alpha = min2(alpha0 + (1.0f - alpha0) * t, 1.0f); else alpha = 1.0f;
+                    C(CF_TOI, c) = alpha;
+                    setCi(CF_KEY, c, key | (CK_TOIFLAG << 16));
+                }
+                if (alpha < minAlpha) { minContact = c; minAlpha = alpha; }
+            }
+            if (minContact < 0 || 1.0f - 10.0f * RB_EPS < minAlpha) break;
+            cnt.c[REM2D_CNT_TOI_EVENTS]++;
+            int mkey = Ci(CF_KEY, minContact);
+            int mb = key_body(mkey), eA = key_edge(mkey);
+            // backups
+            float bk_c0x = B(BF_C0X, mb), bk_c0y = B(BF_C0Y, mb), bk_a0 = B(BF_A0, mb), bk_al = B(BF_ALPHA0, mb);
+            float bk_cx = B(BF_CX, mb), bk_cy = B(BF_CY, mb), bk_a = B(BF_A, mb);
+            float bk_ea = EA(eA);
+            set_edge_alpha(eA, minAlpha);
+            body_advance(mb, minAlpha);
+            contact_update(minContact);
+            mkey = Ci(CF_KEY, minContact);
+            mkey &= ~(CK_TOIFLAG << 16);
+            mkey += 1 << 24;                                       // ++toiCount
+            setCi(CF_KEY, minContact, mkey);
+            if (!(key_flags(mkey) & CK_ENABLED) || !(key_flags(mkey) & CK_TOUCHING)) {
+                setCi(CF_KEY, minContact, mkey & ~(CK_ENABLED << 16));
+                EA(eA) = bk_ea;
+                B(BF_C0X, mb) = bk_c0x; B(BF_C0Y, mb) = bk_c0y; B(BF_A0, mb) = bk_a0; B(BF_ALPHA0, mb) = bk_al;
+                B(BF_CX, mb) = bk_cx; B(BF_CY, mb) = bk_cy; B(BF_A, mb) = bk_a;
+                sync_transform(mb);
+                continue;
+            }
+            set_awake(mb, true);
+            // TOI mini-island: this module + its touching contacts (joints are NOT part of it)
+            int isl[RB_TOI_ISLAND_CAP]; int ni = 0;
+            isl[ni++] = minContact;
+            setCi(CF_KEY, minContact, mkey | (CK_ISLAND << 16));
+            for (int c = nc - 1; c >= 0; --c) {
+                int key = Ci(CF_KEY, c);
+                if (key_body(key) != mb) continue;
+                if (key_flags(key) & CK_ISLAND) continue;
+                if (ni == RB_TOI_ISLAND_CAP) { setSi(S_STATUS, Si(S_STATUS) | ST_TOI_OVERFLOW); break; }
+                int e = key_edge(key);
+                bool inIsland = false;
+                for (int i = 0; i < ni; ++i) inIsland |= (key_edge(Ci(CF_KEY, isl[i])) == e);
+                float backup = EA(e);
+                if (!inIsland) set_edge_alpha(e, minAlpha);
+                contact_update(c);
+                key = Ci(CF_KEY, c);
+                if (!(key_flags(key) & CK_ENABLED) || !(key_flags(key) & CK_TOUCHING)) { EA(e) = backup; continue; }
+                setCi(CF_KEY, c, key | (CK_ISLAND << 16));
+                isl[ni++] = c;
+            }
+            float subDt = (1.0f - minAlpha) * dt;
+            // b2Island::SolveTOI: only the module moves
+            float mB = B(BF_INVM, mb), iB = B(BF_INVI, mb);
+            HB(HB_INVM, mb) = mB; HB(HB_INVI, mb) = iB;
+            HB(HB_VX, mb) = B(BF_CX, mb); HB(HB_VY, mb) = B(BF_CY, mb); HB(HB_W, mb) = B(BF_A, mb);   // position overlay
+            int nt = ni < NT ? ni : NT;
+            if (ni > NT) setSi(S_STATUS, Si(S_STATUS) | ST_HOT_OVERFLOW);
+            for (int t = 0; t < nt; ++t) contact_init_position(t, isl[t]);
+            for (int it = 0; it < 20; ++it) {
+                float minSep = 0.0f;
+                for (int t = 0; t < nt; ++t) minSep = contact_solve_position(t, RB_TOI_BAUMGARTE, minSep);
+                if (minSep >= -1.5f * RB_LINEAR_SLOP) break;
+            }
+            V2 cB = mk(HB(HB_VX, mb), HB(HB_VY, mb)); float aB = HB(HB_W, mb);
+            B(BF_C0X, mb) = cB.x; B(BF_C0Y, mb) = cB.y; B(BF_A0, mb) = aB;      // leap of faith
+            for (int t = 0; t < nt; ++t) contact_init_velocity(t, isl[t], cB, aB, mB, iB, 1.0f, false);
+            HB(HB_VX, mb) = B(BF_VX, mb); HB(HB_VY, mb) = B(BF_VY, mb); HB(HB_W, mb) = B(BF_W, mb);
+            const int vit = k->vel_iters;
+            for (int it = 0; it < vit; ++it)
+                for (int t = 0; t < nt; ++t) contact_solve_velocity(t);
+            count_contact_solves(nt, vit);
+            {
+                V2 v = mk(HB(HB_VX, mb), HB(HB_VY, mb)); float w = HB(HB_W, mb);
+                V2 translation = subDt * v;
+                if (dot(translation, translation) > RB_MAX_TRANS * RB_MAX_TRANS) { float ratio = RB_MAX_TRANS / len(translation); v = ratio * v; }
+                float rotation = subDt * w;
+                if (rotation * rotation > RB_MAX_ROT * RB_MAX_ROT) { float ratio = RB_MAX_ROT / abs2(rotation); w *= ratio; }
+                cB = cB + subDt * v; aB += subDt * w;
+                B(BF_CX, mb) = cB.x; B(BF_CY, mb) = cB.y; B(BF_A, mb) = aB;
+                B(BF_VX, mb) = v.x; B(BF_VY, mb) = v.y; B(BF_W, mb) = w;
+                sync_transform(mb);
+            }
+            synchronize_fixtures(mb);
+            for (int c = 0; c < nc; ++c) {
+                int key = Ci(CF_KEY, c);
+                if (key_body(key) == mb) setCi(CF_KEY, c, key & ~((CK_TOIFLAG | CK_ISLAND) << 16));
+            }
+            find_new_contacts();
+        }
+    }
+
+    // ---- b2World::Step
+    __device__ void world_step() {
+        const float dt = k->dt;
+        if (Si(S_NEWFIX)) { find_new_contacts(); setSi(S_NEWFIX, 0); }
+        float inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+        float dtRatio = S(S_INVDT0) * dt;
+        collide();
+        if (dt > 0.0f) solve(dtRatio);
+        if (k->continuous && dt > 0.0f) solve_toi();
+        if (dt > 0.0f) S(S_INVDT0) = inv_dt;
+    }
+
+    // ---- Modular2D.step + the body of evaluate()'s loop
+    __device__ void tick() {
+        double wod = Sd(S_WOD_LO) + k->wod_speed;
+        setSd(S_WOD_LO, wod);
+        for (int j = 0; j < nj; ++j) {
+            double ist = Jd(JF_ISTATE, j) + Jd(JF_FREQ, j);
+            setJd(JF_ISTATE, j, ist);
+            double s, c;
+            sincos_kernel(ist + (Jd(JF_PHASE, j) + 0.0), s, c);
+            double out = Jd(JF_AMP, j) * s + Jd(JF_OFFS, j);
+            int a = Ji(JF_META, j) & 0xff, b = j + 1;
+            float currentAngle = B(BF_A, b) - B(BF_A, a) - 0.0f;
+            double speed = (out - (double)currentAngle) * k->p_gain;
+            set_awake(a, true); set_awake(b, true);
+            J(JF_MSPEED, j) = (float)speed;
+        }
+        world_step();
+        cnt.c[REM2D_CNT_TICKS]++;
+        int i = Si(S_TICKS);
+        setSi(S_TICKS, i + 1);
+        float x = B(BF_CX, 0);
+        double reward = (double)x;
+        if (k->terminate) {
+            if (x < 0.0f) reward = -100.0;
+            if (wod > (double)x) reward = -100.0;
+            if (reward < -10.0) setSi(S_ALIVE, 0);
+            else if (reward > k->env_length) {
+                reward += (double)(k->evaluation_steps - i) / (double)k->evaluation_steps;
+                setSd(S_FIT_LO, reward);
+                setSi(S_ALIVE, 0);
+            } else if (reward > 0.0) setSd(S_FIT_LO, reward);
+            if (i + 1 >= k->evaluation_steps) setSi(S_ALIVE, 0);
+        } else if (reward > 0.0) setSd(S_FIT_LO, reward);
+    }
+};
+
+}  // namespace rem2d

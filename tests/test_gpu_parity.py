@@ -1,0 +1,90 @@
+"""Parity of the CUDA path against the CPU oracle, through the C-ABI (pin P4). Needs a GPU.
+
+Integer / index results (contact pairs, limit states, tick counts) must be identical; float32 state is
+compared for exact equality as well: both sides perform the same IEEE operations in the same order
+(no FMA contraction, shared portable sin/cos), which is far stricter than the 1e-4 relative bound the
+north star asks for over the first 100 ticks.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from gym_rem2d_b200 import Individual, constants as K, terrain
+from gym_rem2d_b200.capi import Engine
+from gym_rem2d_b200.flatten import flatten_population
+from oracle.oracle import OracleEngine
+
+pytestmark = pytest.mark.gpu
+
+
+def engines(ys, **cfg):
+    g, o = Engine(device=0, **cfg), OracleEngine(threads=8, **cfg)
+    for e in (g, o):
+        e.set_terrain(ys, K.TERRAIN_STEP)
+    return g, o
+
+
+def assert_same_state(sg, so, what):
+    for k in ("alive", "ticks", "limit_state", "n_contacts", "n_touching", "touching_pairs", "awake"):
+        assert np.array_equal(sg[k], so[k]), "%s: %s differs" % (what, k)
+    for k in ("pose", "vel", "joint_impulse", "motor_speed", "touching_impulse", "wod"):
+        same = sg[k] == so[k]
+        assert same.all(), "%s: %s differs in %d of %d values, max abs err %g" % (
+            what, k, (~same).sum(), same.size, np.abs(sg[k].astype(np.float64) - so[k]).max())
+
+
+@pytest.mark.parametrize("enc,flat,n,seed", [("direct", True, 256, 1), ("lsystem", False, 192, 2), ("ce", False, 128, 3)])
+def test_first_100_ticks_bit_exact(enc, flat, n, seed):
+    random.seed(seed)
+    pop = flatten_population([Individual.random(encoding=enc) for _ in range(n)])
+    xs, ys = terrain.flat_terrain() if flat else terrain.generate_terrain()
+    g, o = engines(ys)
+    g.upload(pop); o.upload(pop)
+    assert_same_state(g.read_state(max_pairs=24), o.read_state(max_pairs=24), "tick 0")
+    for t in (1, 1, 1, 7, 10, 30, 50):
+        g.step(t); o.step(t)
+        assert_same_state(g.read_state(max_pairs=24), o.read_state(max_pairs=24), "%s after +%d" % (enc, t))
+
+
+@pytest.mark.parametrize("enc,n,seed", [("direct", 512, 11), ("lsystem", 512, 12), ("ce", 256, 13)])
+def test_full_episode_fitness_identical(enc, n, seed):
+    random.seed(seed)
+    pop = flatten_population([Individual.random(encoding=enc) for _ in range(n)])
+    xs, ys = terrain.generate_terrain()
+    g, o = engines(ys)
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    fo, to = o.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to)
+    assert np.array_equal(fg, fo)
+    assert g.counters() == o.counters()
+    assert tg.min() >= 20 and fg.max() > 5.0
+
+
+def test_fixed_horizon_and_reset_reproducible():
+    random.seed(21)
+    pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(96)])
+    xs, ys = terrain.generate_terrain()
+    g, o = engines(ys, terminate=0)
+    g.upload(pop); o.upload(pop)
+    g.step(300); o.step(300)
+    s1 = g.read_state(max_pairs=24)
+    assert_same_state(s1, o.read_state(max_pairs=24), "fixed horizon 300")
+    assert (s1["ticks"] == 300).all()
+    g.reset(); g.step(300)
+    assert_same_state(g.read_state(max_pairs=24), s1, "after reset")
+
+
+def test_single_body_creatures_sleep_and_die_like_the_oracle():
+    random.seed(5)
+    inds = [Individual.random(encoding="ce") for _ in range(200)]
+    pop = flatten_population(inds)
+    keep = np.nonzero(np.diff(pop.body_off) == 1)[0][:64]
+    assert len(keep) >= 16
+    sub = pop.select(keep)
+    xs, ys = terrain.generate_terrain()
+    g, o = engines(ys)
+    g.upload(sub); o.upload(sub)
+    for _ in range(5):
+        g.step(30); o.step(30)
+        assert_same_state(g.read_state(max_pairs=8), o.read_state(max_pairs=8), "single-body")
