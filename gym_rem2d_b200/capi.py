@@ -78,6 +78,7 @@ def load_library(path=None):
     lib.rem2d_evaluate.argtypes = [H, C.POINTER(Population), C.c_int32, C.c_void_p, C.c_void_p]
     lib.rem2d_last_step_ms.argtypes = [H]
     lib.rem2d_last_step_ms.restype = C.c_float
+    lib.rem2d_measure_fp32_peak.argtypes = [H, C.POINTER(C.c_double)]
     lib.rem2d_launch_count.argtypes = [H]
     lib.rem2d_launch_count.restype = C.c_int64
     _LIBS[path] = lib
@@ -182,6 +183,12 @@ class Engine:
 
     def last_step_ms(self):
         return float(self.lib.rem2d_last_step_ms(self.h))
+
+    def measure_fp32_peak(self):
+        """GFLOP/s of non-fused FP32 multiply/add issue on this device (CUDA build only)."""
+        v = C.c_double(0.0)
+        self._check(self.lib.rem2d_measure_fp32_peak(self.h, C.byref(v)), "rem2d_measure_fp32_peak")
+        return v.value
 
     def launch_count(self):
         return int(self.lib.rem2d_launch_count(self.h))

@@ -17,17 +17,18 @@
 using namespace rem2d;
 
 // ------------------------------------------------------------------ capacity classes
-// NB bodies, NC contact-pool slots (fat-AABB overlaps), NT touching contacts staged in shared memory.
+// NB bodies, NC contact-pool slots (fat-AABB overlaps), NT touching contacts staged in shared memory
+// (further touching contacts, up to NC, spill to the cold block: correct but slower).
 // hot words/lane = 5*NB + 18*(NB-1) + 21*NT; one warp needs 128 B per word.
 #define REM2D_CLASSES(X) \
-    X(0, 2, 12, 4)       \
-    X(1, 4, 24, 6)       \
-    X(2, 8, 40, 10)      \
-    X(3, 12, 56, 14)     \
-    X(4, 16, 72, 18)     \
-    X(5, 22, 96, 24)     \
-    X(6, 32, 128, 34)    \
-    X(7, 44, 160, 34)
+    X(0, 2, 16, 4)       \
+    X(1, 4, 28, 6)       \
+    X(2, 8, 48, 10)      \
+    X(3, 12, 64, 12)     \
+    X(4, 16, 80, 16)     \
+    X(5, 22, 104, 20)    \
+    X(6, 32, 144, 28)    \
+    X(7, 44, 192, 34)
 #define N_CLASSES 8
 
 struct ClassInfo { int nb, nc, nt, nj, off_body, off_joint, off_cont, off_edge, words, hot_words; };
@@ -169,6 +170,17 @@ __global__ void gather_kernel(const float* state, const int* __restrict__ lane_c
     ticks[c] = __float_as_int(g[S_TICKS * 32]);
     alive[c] = __float_as_int(g[S_ALIVE * 32]);
     status[c] = __float_as_int(g[S_STATUS * 32]);
+}
+
+// FP32 issue-rate microbenchmark: 8 independent multiply / add chains per thread. The step kernel is built with
+// -fmad=false (parity), so its ceiling is the non-fused FMUL/FADD issue rate: 1 FLOP per lane per cycle.
+__global__ void fp32_issue_kernel(float* out, int iters, float b, float c) {
+    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * b; a1 = a1 * b; a2 = a2 * b; a3 = a3 * b; a4 = a4 * b; a5 = a5 * b; a6 = a6 * b; a7 = a7 * b;
+        a0 = a0 + c; a1 = a1 + c; a2 = a2 + c; a3 = a3 + c; a4 = a4 + c; a5 = a5 + c; a6 = a6 + c; a7 = a7 + c;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 // ------------------------------------------------------------------ handle
@@ -511,7 +523,7 @@ static int gather(rem2d_handle* h) {
     for (int c = 0; c < n; ++c)
         if (h->h_status[c]) {
             char buf[200];
-            snprintf(buf, sizeof(buf), "creature %d exceeded a capacity of its class (status %d: 1 contact pool, 2 touching contacts, 4 TOI island)", c, h->h_status[c]);
+            snprintf(buf, sizeof(buf), "creature %d exceeded a capacity of its class (status %d: 1 contact pool, 4 TOI island)", c, h->h_status[c]);
             h->err = buf;
             return REM2D_E_CAPACITY;
         }
@@ -577,6 +589,31 @@ int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_tic
     if (rc) return rc;
     if (fitness_out) memcpy(fitness_out, h->h_fitness.data(), sizeof(double) * h->n_creatures);
     if (ticks_out) memcpy(ticks_out, h->h_ticks.data(), sizeof(int) * h->n_creatures);
+    return REM2D_OK;
+}
+
+// Measured non-fused FP32 issue peak of this device in GFLOP/s (best of 5), for the roofline denominator.
+int rem2d_measure_fp32_peak(rem2d_handle* h, double* gflops) {
+    if (!h || !gflops) return REM2D_E_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    float* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(float) * blocks * threads));
+    double best = 0.0;
+    for (int r = 0; r < 6; ++r) {
+        CK(cudaEventRecord(h->ev_start, h->user_stream));
+        fp32_issue_kernel<<<blocks, threads, 0, h->user_stream>>>(d, iters, 1.0000001f, 1e-7f);
+        CK(cudaEventRecord(h->ev_stop, h->user_stream));
+        CK(cudaEventSynchronize(h->ev_stop));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+        double gf = (double)blocks * threads * iters * 16.0 / (ms * 1e-3) / 1e9;
+        if (r > 0 && gf > best) best = gf;
+    }
+    cudaFree(d);
+    *gflops = best;
     return REM2D_OK;
 }
 

@@ -143,7 +143,6 @@ enum { CF_KEY, CF_TOI, CF_LNX, CF_LNY, CF_LPX, CF_LPY, CF_P0X, CF_P0Y, CF_P0N, C
 #define MT_FACE_B 2
 // status bits
 #define ST_POOL_OVERFLOW 1     // contact pool (NC) exhausted
-#define ST_HOT_OVERFLOW 2      // touching-contact capacity of the shared-memory stage (NT) exhausted
 #define ST_TOI_OVERFLOW 4      // TOI mini-island larger than RB_TOI_ISLAND_CAP
 
 // hot (shared memory) layout, words per lane: 5*NB + 18*NJ + 21*NT
@@ -180,7 +179,9 @@ struct Sim {
     static constexpr int OFF_JOINT = OFF_BODY + BF_COUNT * NB;
     static constexpr int OFF_CONT = OFF_JOINT + JF_COUNT * NJ;
     static constexpr int OFF_EDGE = OFF_CONT + CF_COUNT * NC;      // alpha0 of the static edge bodies
-    static constexpr int WORDS = OFF_EDGE + RB_MAX_EDGES;
+    static constexpr int NS = NC - NT;                              // touching contacts beyond NT spill to HBM
+    static constexpr int OFF_SPILL = OFF_EDGE + RB_MAX_EDGES;
+    static constexpr int WORDS = OFF_SPILL + HC_COUNT * NS;
     static constexpr int HOFF_JOINT = HB_COUNT * NB;
     static constexpr int HOFF_CONT = HOFF_JOINT + HJ_COUNT * NJ;
     static constexpr int HOT_WORDS = HOFF_CONT + HC_COUNT * NT;
@@ -213,8 +214,19 @@ struct Sim {
     __device__ __forceinline__ float& HB(int f, int i) { return h[(f * NB + i) * 32]; }
     __device__ __forceinline__ float& HJ(int f, int j) { return h[(HOFF_JOINT + f * NJ + j) * 32]; }
     __device__ __forceinline__ int HJi(int f, int j) { return __float_as_int(HJ(f, j)); }
-    __device__ __forceinline__ float& HC(int f, int c) { return h[(HOFF_CONT + f * NT + c) * 32]; }
-    __device__ __forceinline__ int HCi(int f, int c) { return __float_as_int(HC(f, c)); }
+    // Hot contact slot t: shared memory for t < NT, a spill region of the cold block otherwise. The two
+    // call sites of for_contacts() are specialised by the compiler (LDS/STS vs LDG/STG).
+    template <class F>
+    __device__ __forceinline__ void for_contacts(int nt, F f) {
+        const int n1 = nt < NT ? nt : NT;
+        for (int t = 0; t < n1; ++t) f(h + (HOFF_CONT + t) * 32, NT * 32, t);
+        for (int t = NT; t < nt; ++t) f(g + (OFF_SPILL + (t - NT)) * 32, NS * 32, t);
+    }
+    template <class F>
+    __device__ __forceinline__ void with_contact(int t, F f) {
+        if (t < NT) f(h + (HOFF_CONT + t) * 32, NT * 32);
+        else f(g + (OFF_SPILL + (t - NT)) * 32, NS * 32);
+    }
 
     __device__ __forceinline__ int key_body(int key) { return key & 0xff; }
     __device__ __forceinline__ int key_edge(int key) { return (key >> 8) & 0xff; }
@@ -506,7 +518,7 @@ struct Sim {
     // ---- contact constraints in shared memory
     // Build the velocity constraint of pool contact c in hot slot t from the CURRENT solver pose of its body
     // (b2ContactSolver ctor + InitializeVelocityConstraints). cB/aB are passed in.
-    __device__ __forceinline__ void contact_init_velocity(int t, int c, V2 cB, float aB, float mB, float iB, float dtRatio, bool warm) {
+    __device__ __forceinline__ void contact_init_velocity(float* hc, const int st, int c, V2 cB, float aB, float mB, float iB, float dtRatio, bool warm) {
         int key = Ci(CF_KEY, c);
         int b = key_body(key);
         int flags = key_flags(key);
@@ -553,91 +565,91 @@ struct Sim {
         V2 r0 = wp0 - cB, r1 = wp1 - cB;
         float rn0 = cross(r0, normal), rt0 = cross(r0, tangent);
         float kN0 = mB + iB * rn0 * rn0, kT0 = mB + iB * rt0 * rt0;
-        HC(HC_NX, t) = normal.x; HC(HC_NY, t) = normal.y;
-        HC(HC_R0X, t) = r0.x; HC(HC_R0Y, t) = r0.y;
-        HC(HC_NM0, t) = kN0 > 0.0f ? 1.0f / kN0 : 0.0f;
-        HC(HC_TM0, t) = kT0 > 0.0f ? 1.0f / kT0 : 0.0f;
-        HC(HC_NI0, t) = warm ? dtRatio * C(CF_P0N, c) : 0.0f;
-        HC(HC_TI0, t) = warm ? dtRatio * C(CF_P0T, c) : 0.0f;
+        hc[HC_NX * st] = normal.x; hc[HC_NY * st] = normal.y;
+        hc[HC_R0X * st] = r0.x; hc[HC_R0Y * st] = r0.y;
+        hc[HC_NM0 * st] = kN0 > 0.0f ? 1.0f / kN0 : 0.0f;
+        hc[HC_TM0 * st] = kT0 > 0.0f ? 1.0f / kT0 : 0.0f;
+        hc[HC_NI0 * st] = warm ? dtRatio * C(CF_P0N, c) : 0.0f;
+        hc[HC_TI0 * st] = warm ? dtRatio * C(CF_P0T, c) : 0.0f;
         int vcount = count;
         if (count > 1) {
             float rn1 = cross(r1, normal), rt1 = cross(r1, tangent);
             float kN1 = mB + iB * rn1 * rn1, kT1 = mB + iB * rt1 * rt1;
-            HC(HC_R1X, t) = r1.x; HC(HC_R1Y, t) = r1.y;
-            HC(HC_NM1, t) = kN1 > 0.0f ? 1.0f / kN1 : 0.0f;
-            HC(HC_TM1, t) = kT1 > 0.0f ? 1.0f / kT1 : 0.0f;
-            HC(HC_NI1, t) = warm ? dtRatio * C(CF_P1N, c) : 0.0f;
-            HC(HC_TI1, t) = warm ? dtRatio * C(CF_P1T, c) : 0.0f;
+            hc[HC_R1X * st] = r1.x; hc[HC_R1Y * st] = r1.y;
+            hc[HC_NM1 * st] = kN1 > 0.0f ? 1.0f / kN1 : 0.0f;
+            hc[HC_TM1 * st] = kT1 > 0.0f ? 1.0f / kT1 : 0.0f;
+            hc[HC_NI1 * st] = warm ? dtRatio * C(CF_P1N, c) : 0.0f;
+            hc[HC_TI1 * st] = warm ? dtRatio * C(CF_P1T, c) : 0.0f;
             float k11 = mB + iB * rn0 * rn0, k22 = mB + iB * rn1 * rn1, k12 = mB + iB * rn0 * rn1;
             if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
-                HC(HC_K11, t) = k11; HC(HC_K12, t) = k12; HC(HC_K22, t) = k22;
+                hc[HC_K11 * st] = k11; hc[HC_K12 * st] = k12; hc[HC_K22 * st] = k22;
                 float det = k11 * k22 - k12 * k12;
                 if (det != 0.0f) det = 1.0f / det;
-                HC(HC_IXX, t) = det * k22; HC(HC_IXY, t) = -det * k12; HC(HC_IYY, t) = det * k11;
+                hc[HC_IXX * st] = det * k22; hc[HC_IXY * st] = -det * k12; hc[HC_IYY * st] = det * k11;
             } else vcount = 1;
         }
-        HC(HC_META, t) = __int_as_float(b | (vcount << 8) | (c << 16));
+        hc[HC_META * st] = __int_as_float(b | (vcount << 8) | (c << 16));
     }
 
     // one sequential-impulse pass over hot contact slot t (b2ContactSolver::SolveVelocityConstraints)
-    __device__ __forceinline__ void contact_solve_velocity(int t) {
-        int meta = HCi(HC_META, t);
+    __device__ __forceinline__ void contact_solve_velocity(float* hc, const int st) {
+        int meta = __float_as_int(hc[HC_META * st]);
         int b = meta & 0xff, count = (meta >> 8) & 3;
         float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
         V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
-        V2 normal = mk(HC(HC_NX, t), HC(HC_NY, t)), tangent = cross_vs(normal, 1.0f);
+        V2 normal = mk(hc[HC_NX * st], hc[HC_NY * st]), tangent = cross_vs(normal, 1.0f);
         const float friction = k->friction;
-        V2 r0 = mk(HC(HC_R0X, t), HC(HC_R0Y, t));
+        V2 r0 = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
         {   // friction, point 0
             V2 dv = vB + cross_sv(wB, r0);
             float vt = dot(dv, tangent);
-            float lambda = HC(HC_TM0, t) * (-vt);
-            float ti = HC(HC_TI0, t);
-            float maxF = friction * HC(HC_NI0, t);
+            float lambda = hc[HC_TM0 * st] * (-vt);
+            float ti = hc[HC_TI0 * st];
+            float maxF = friction * hc[HC_NI0 * st];
             float ni = clampf(ti + lambda, -maxF, maxF);
-            lambda = ni - ti; HC(HC_TI0, t) = ni;
+            lambda = ni - ti; hc[HC_TI0 * st] = ni;
             V2 P = lambda * tangent;
             vB = vB + mB * P; wB += iB * cross(r0, P);
         }
         if (count == 1) {
             V2 dv = vB + cross_sv(wB, r0);
             float vn = dot(dv, normal);
-            float lambda = -HC(HC_NM0, t) * vn;
-            float ni0 = HC(HC_NI0, t);
+            float lambda = -hc[HC_NM0 * st] * vn;
+            float ni0 = hc[HC_NI0 * st];
             float ni = max2(ni0 + lambda, 0.0f);
-            lambda = ni - ni0; HC(HC_NI0, t) = ni;
+            lambda = ni - ni0; hc[HC_NI0 * st] = ni;
             V2 P = lambda * normal;
             vB = vB + mB * P; wB += iB * cross(r0, P);
         } else {
-            V2 r1 = mk(HC(HC_R1X, t), HC(HC_R1Y, t));
+            V2 r1 = mk(hc[HC_R1X * st], hc[HC_R1Y * st]);
             {   // friction, point 1
                 V2 dv = vB + cross_sv(wB, r1);
                 float vt = dot(dv, tangent);
-                float lambda = HC(HC_TM1, t) * (-vt);
-                float ti = HC(HC_TI1, t);
-                float maxF = friction * HC(HC_NI1, t);
+                float lambda = hc[HC_TM1 * st] * (-vt);
+                float ti = hc[HC_TI1 * st];
+                float maxF = friction * hc[HC_NI1 * st];
                 float ni = clampf(ti + lambda, -maxF, maxF);
-                lambda = ni - ti; HC(HC_TI1, t) = ni;
+                lambda = ni - ti; hc[HC_TI1 * st] = ni;
                 V2 P = lambda * tangent;
                 vB = vB + mB * P; wB += iB * cross(r1, P);
             }
-            float a1 = HC(HC_NI0, t), a2 = HC(HC_NI1, t);
+            float a1 = hc[HC_NI0 * st], a2 = hc[HC_NI1 * st];
             V2 dv1 = vB + cross_sv(wB, r0), dv2 = vB + cross_sv(wB, r1);
             float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-            float k11 = HC(HC_K11, t), k12 = HC(HC_K12, t), k22 = HC(HC_K22, t);
+            float k11 = hc[HC_K11 * st], k12 = hc[HC_K12 * st], k22 = hc[HC_K22 * st];
             float bx = vn1 - (k11 * a1 + k12 * a2), by = vn2 - (k12 * a1 + k22 * a2);
             float x1, x2; bool solved = false;
-            x1 = -(HC(HC_IXX, t) * bx + HC(HC_IXY, t) * by); x2 = -(HC(HC_IXY, t) * bx + HC(HC_IYY, t) * by);
+            x1 = -(hc[HC_IXX * st] * bx + hc[HC_IXY * st] * by); x2 = -(hc[HC_IXY * st] * bx + hc[HC_IYY * st] * by);
             if (x1 >= 0.0f && x2 >= 0.0f) solved = true;
-            if (!solved) { x1 = -HC(HC_NM0, t) * bx; x2 = 0.0f; vn2 = k12 * x1 + by; if (x1 >= 0.0f && vn2 >= 0.0f) solved = true; }
-            if (!solved) { x1 = 0.0f; x2 = -HC(HC_NM1, t) * by; vn1 = k12 * x2 + bx; if (x2 >= 0.0f && vn1 >= 0.0f) solved = true; }
+            if (!solved) { x1 = -hc[HC_NM0 * st] * bx; x2 = 0.0f; vn2 = k12 * x1 + by; if (x1 >= 0.0f && vn2 >= 0.0f) solved = true; }
+            if (!solved) { x1 = 0.0f; x2 = -hc[HC_NM1 * st] * by; vn1 = k12 * x2 + bx; if (x2 >= 0.0f && vn1 >= 0.0f) solved = true; }
             if (!solved) { x1 = 0.0f; x2 = 0.0f; if (bx >= 0.0f && by >= 0.0f) solved = true; }
             if (solved) {
                 float d1 = x1 - a1, d2 = x2 - a2;
                 V2 P1 = d1 * normal, P2 = d2 * normal;
                 vB = vB + mB * (P1 + P2);
                 wB += iB * (cross(r0, P1) + cross(r1, P2));
-                HC(HC_NI0, t) = x1; HC(HC_NI1, t) = x2;
+                hc[HC_NI0 * st] = x1; hc[HC_NI1 * st] = x2;
             }
         }
         HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
@@ -645,30 +657,30 @@ struct Sim {
 
     __device__ __forceinline__ void count_contact_solves(int nt, int vit) {
         int n1 = 0, n2 = 0;
-        for (int t = 0; t < nt; ++t) { if (((HCi(HC_META, t) >> 8) & 3) == 1) ++n1; else ++n2; }
+        for_contacts(nt, [&](float* hc, const int st, int) { if (((__float_as_int(hc[HC_META * st]) >> 8) & 3) == 1) ++n1; else ++n2; });
         cnt.c[REM2D_CNT_P1_VSOLVES] += (unsigned)(n1 * vit);
         cnt.c[REM2D_CNT_M2_VSOLVES] += (unsigned)(n2 * vit);
     }
     // position manifold of point j of hot (position overlay) slot t; returns separation
-    __device__ __forceinline__ float psm(int t, int type, int j, V2 cB, float aB, V2& normal, V2& point) {
+    __device__ __forceinline__ float psm(const float* hc, const int st, int type, int j, V2 cB, float aB, V2& normal, V2& point) {
         Rot qB = rot_set(aB);
-        V2 lp = mk(HC(PC_LPX, t), HC(PC_LPY, t));
-        V2 lpt = j == 0 ? mk(HC(PC_P0X, t), HC(PC_P0Y, t)) : mk(HC(PC_P1X, t), HC(PC_P1Y, t));
+        V2 lp = mk(hc[PC_LPX * st], hc[PC_LPY * st]);
+        V2 lpt = j == 0 ? mk(hc[PC_P0X * st], hc[PC_P0Y * st]) : mk(hc[PC_P1X * st], hc[PC_P1Y * st]);
         const float radiusA = RB_POLY_RADIUS;
-        float radiusB = HC(PC_RADB, t);
+        float radiusB = hc[PC_RADB * st];
         if (type == MT_CIRCLES) {
-            V2 pointA = lp, pointB = xmul(cB, qB, mk(HC(PC_P0X, t), HC(PC_P0Y, t)));
+            V2 pointA = lp, pointB = xmul(cB, qB, mk(hc[PC_P0X * st], hc[PC_P0Y * st]));
             normal = pointB - pointA;
             normalize(normal);
             point = 0.5f * (pointA + pointB);
             return dot(pointB - pointA, normal) - radiusA - radiusB;
         } else if (type == MT_FACE_A) {
-            normal = mk(HC(PC_LNX, t), HC(PC_LNY, t));
+            normal = mk(hc[PC_LNX * st], hc[PC_LNY * st]);
             V2 clip = xmul(cB, qB, lpt);
             point = clip;
             return dot(clip - lp, normal) - radiusA - radiusB;
         } else {
-            V2 nrm = rmul(qB, mk(HC(PC_LNX, t), HC(PC_LNY, t)));
+            V2 nrm = rmul(qB, mk(hc[PC_LNX * st], hc[PC_LNY * st]));
             V2 planePoint = xmul(cB, qB, lp);
             V2 clip = lpt;
             float sep = dot(clip - planePoint, nrm) - radiusA - radiusB;
@@ -678,15 +690,15 @@ struct Sim {
         }
     }
     // one pass of Solve(TOI)PositionConstraints over hot slot t; returns the min separation seen
-    __device__ __forceinline__ float contact_solve_position(int t, float baumgarte, float minSeparation) {
-        int meta = HCi(PC_META, t);
+    __device__ __forceinline__ float contact_solve_position(float* hc, const int st, float baumgarte, float minSeparation) {
+        int meta = __float_as_int(hc[PC_META * st]);
         int b = meta & 0xff, count = (meta >> 8) & 3, type = (meta >> 10) & 3;
         float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
         V2 cB = mk(HB(HB_VX, b), HB(HB_VY, b)); float aB = HB(HB_W, b);     // position overlay: c, a
         for (int j = 0; j < count; ++j) {
             cnt.c[REM2D_CNT_POINT_PSOLVES]++;
             V2 normal, point;
-            float separation = psm(t, type, j, cB, aB, normal, point);
+            float separation = psm(hc, st, type, j, cB, aB, normal, point);
             V2 rB = point - cB;
             minSeparation = min2(minSeparation, separation);
             float Cc = clampf(baumgarte * (separation + RB_LINEAR_SLOP), -RB_MAX_LIN_CORR, 0.0f);
@@ -700,16 +712,16 @@ struct Sim {
         return minSeparation;
     }
     // copy the position-constraint data of pool contact c into hot slot t
-    __device__ __forceinline__ void contact_init_position(int t, int c) {
+    __device__ __forceinline__ void contact_init_position(float* hc, const int st, int c) {
         int key = Ci(CF_KEY, c);
         int b = key_body(key), flags = key_flags(key);
         int type = (flags >> CK_TYPE_SHIFT) & 3, count = (flags >> CK_COUNT_SHIFT) & 3;
-        HC(PC_META, t) = __int_as_float(b | (count << 8) | (type << 10));
-        HC(PC_LNX, t) = C(CF_LNX, c); HC(PC_LNY, t) = C(CF_LNY, c);
-        HC(PC_LPX, t) = C(CF_LPX, c); HC(PC_LPY, t) = C(CF_LPY, c);
-        HC(PC_P0X, t) = C(CF_P0X, c); HC(PC_P0Y, t) = C(CF_P0Y, c);
-        HC(PC_P1X, t) = C(CF_P1X, c); HC(PC_P1Y, t) = C(CF_P1Y, c);
-        HC(PC_RADB, t) = (Bi(BF_FLAGS, b) & BFL_CIRCLE) ? B(BF_HX, b) : RB_POLY_RADIUS;
+        hc[PC_META * st] = __int_as_float(b | (count << 8) | (type << 10));
+        hc[PC_LNX * st] = C(CF_LNX, c); hc[PC_LNY * st] = C(CF_LNY, c);
+        hc[PC_LPX * st] = C(CF_LPX, c); hc[PC_LPY * st] = C(CF_LPY, c);
+        hc[PC_P0X * st] = C(CF_P0X, c); hc[PC_P0Y * st] = C(CF_P0Y, c);
+        hc[PC_P1X * st] = C(CF_P1X, c); hc[PC_P1Y * st] = C(CF_P1Y, c);
+        hc[PC_RADB * st] = (Bi(BF_FLAGS, b) & BFL_CIRCLE) ? B(BF_HX, b) : RB_POLY_RADIUS;
     }
 
     // ---- revolute joints in shared memory (b2RevoluteJoint)
@@ -849,30 +861,31 @@ struct Sim {
             int key = Ci(CF_KEY, c);
             int fl = key_flags(key);
             if (!(fl & CK_ENABLED) || !(fl & CK_TOUCHING)) continue;
-            if (nt == NT) { setSi(S_STATUS, Si(S_STATUS) | ST_HOT_OVERFLOW); break; }
             int b = key_body(key);
-            contact_init_velocity(nt, c, mk(B(BF_CX, b), B(BF_CY, b)), B(BF_A, b), B(BF_INVM, b), B(BF_INVI, b), dtRatio, true);
+            with_contact(nt, [&](float* hc, const int st) {
+                contact_init_velocity(hc, st, c, mk(B(BF_CX, b), B(BF_CY, b)), B(BF_A, b), B(BF_INVM, b), B(BF_INVI, b), dtRatio, true);
+            });
             ++nt;
         }
         // warm start contacts
-        for (int t = 0; t < nt; ++t) {
-            int meta = HCi(HC_META, t);
+        for_contacts(nt, [&](float* hc, const int st, int) {
+            int meta = __float_as_int(hc[HC_META * st]);
             int b = meta & 0xff, count = (meta >> 8) & 3;
             float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
             V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
-            V2 normal = mk(HC(HC_NX, t), HC(HC_NY, t)), tangent = cross_vs(normal, 1.0f);
+            V2 normal = mk(hc[HC_NX * st], hc[HC_NY * st]), tangent = cross_vs(normal, 1.0f);
             {
-                V2 r = mk(HC(HC_R0X, t), HC(HC_R0Y, t));
-                V2 P = HC(HC_NI0, t) * normal + HC(HC_TI0, t) * tangent;
+                V2 r = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
+                V2 P = hc[HC_NI0 * st] * normal + hc[HC_TI0 * st] * tangent;
                 wB += iB * cross(r, P); vB = vB + mB * P;
             }
             if (count > 1) {
-                V2 r = mk(HC(HC_R1X, t), HC(HC_R1Y, t));
-                V2 P = HC(HC_NI1, t) * normal + HC(HC_TI1, t) * tangent;
+                V2 r = mk(hc[HC_R1X * st], hc[HC_R1Y * st]);
+                V2 P = hc[HC_NI1 * st] * normal + hc[HC_TI1 * st] * tangent;
                 wB += iB * cross(r, P); vB = vB + mB * P;
             }
             HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
-        }
+        });
         // joints: InitVelocityConstraints in island order (slot s = s-th joint of the island)
         for (int s = 0; s < nj; ++s) {
             int jm = Ji(JF_META, s);
@@ -920,17 +933,17 @@ struct Sim {
         const int vit = k->vel_iters;
         for (int it = 0; it < vit; ++it) {
             for (int s = 0; s < nj; ++s) joint_solve_velocity(s);
-            for (int t = 0; t < nt; ++t) contact_solve_velocity(t);
+            for_contacts(nt, [&](float* hc, const int st, int) { contact_solve_velocity(hc, st); });
         }
         cnt.c[REM2D_CNT_JOINT_VSOLVES] += (unsigned)(vit * nj);
         count_contact_solves(nt, vit);
         // store impulses
-        for (int t = 0; t < nt; ++t) {
-            int meta = HCi(HC_META, t);
+        for_contacts(nt, [&](float* hc, const int st, int) {
+            int meta = __float_as_int(hc[HC_META * st]);
             int c = (meta >> 16) & 0xffff, count = (meta >> 8) & 3;
-            C(CF_P0N, c) = HC(HC_NI0, t); C(CF_P0T, c) = HC(HC_TI0, t);
-            if (count > 1) { C(CF_P1N, c) = HC(HC_NI1, t); C(CF_P1T, c) = HC(HC_TI1, t); }
-        }
+            C(CF_P0N, c) = hc[HC_NI0 * st]; C(CF_P0T, c) = hc[HC_TI0 * st];
+            if (count > 1) { C(CF_P1N, c) = hc[HC_NI1 * st]; C(CF_P1T, c) = hc[HC_TI1 * st]; }
+        });
         for (int s = 0; s < nj; ++s) {
             int j = (HJi(HJ_META, s) >> 24) & 0xff;
             J(JF_IMPX, j) = HJ(HJ_IMPX, s); J(JF_IMPY, j) = HJ(HJ_IMPY, s); J(JF_IMPZ, j) = HJ(HJ_IMPZ, s);
@@ -962,15 +975,15 @@ struct Sim {
             HJ(PJ_LABX, s) = J(JF_LABX, j); HJ(PJ_LABY, s) = J(JF_LABY, j);
             HJ(PJ_LOWER, s) = J(JF_LOWER, j); HJ(PJ_UPPER, s) = J(JF_UPPER, j);
         }
-        for (int t = 0; t < nt; ++t) {
-            int c = (HCi(HC_META, t) >> 16) & 0xffff;
-            contact_init_position(t, c);
-        }
+        for_contacts(nt, [&](float* hc, const int st, int) {
+            int c = (__float_as_int(hc[HC_META * st]) >> 16) & 0xffff;
+            contact_init_position(hc, st, c);
+        });
         bool positionSolved = false;
         const int pit = k->pos_iters;
         for (int it = 0; it < pit; ++it) {
             float minSep = 0.0f;
-            for (int t = 0; t < nt; ++t) minSep = contact_solve_position(t, RB_BAUMGARTE, minSep);
+            for_contacts(nt, [&](float* hc, const int st, int) { minSep = contact_solve_position(hc, st, RB_BAUMGARTE, minSep); });
             bool contactsOkay = minSep >= -3.0f * RB_LINEAR_SLOP;
             bool jointsOkay = true;
             for (int s = 0; s < nj; ++s) { bool ok = joint_solve_position(s); jointsOkay = jointsOkay && ok; }
@@ -1330,21 +1343,20 @@ struct Sim {
             float mB = B(BF_INVM, mb), iB = B(BF_INVI, mb);
             HB(HB_INVM, mb) = mB; HB(HB_INVI, mb) = iB;
             HB(HB_VX, mb) = B(BF_CX, mb); HB(HB_VY, mb) = B(BF_CY, mb); HB(HB_W, mb) = B(BF_A, mb);   // position overlay
-            int nt = ni < NT ? ni : NT;
-            if (ni > NT) setSi(S_STATUS, Si(S_STATUS) | ST_HOT_OVERFLOW);
-            for (int t = 0; t < nt; ++t) contact_init_position(t, isl[t]);
+            const int nt = ni;
+            for_contacts(nt, [&](float* hc, const int st, int t) { contact_init_position(hc, st, isl[t]); });
             for (int it = 0; it < 20; ++it) {
                 float minSep = 0.0f;
-                for (int t = 0; t < nt; ++t) minSep = contact_solve_position(t, RB_TOI_BAUMGARTE, minSep);
+                for_contacts(nt, [&](float* hc, const int st, int) { minSep = contact_solve_position(hc, st, RB_TOI_BAUMGARTE, minSep); });
                 if (minSep >= -1.5f * RB_LINEAR_SLOP) break;
             }
             V2 cB = mk(HB(HB_VX, mb), HB(HB_VY, mb)); float aB = HB(HB_W, mb);
             B(BF_C0X, mb) = cB.x; B(BF_C0Y, mb) = cB.y; B(BF_A0, mb) = aB;      // leap of faith
-            for (int t = 0; t < nt; ++t) contact_init_velocity(t, isl[t], cB, aB, mB, iB, 1.0f, false);
+            for_contacts(nt, [&](float* hc, const int st, int t) { contact_init_velocity(hc, st, isl[t], cB, aB, mB, iB, 1.0f, false); });
             HB(HB_VX, mb) = B(BF_VX, mb); HB(HB_VY, mb) = B(BF_VY, mb); HB(HB_W, mb) = B(BF_W, mb);
             const int vit = k->vel_iters;
             for (int it = 0; it < vit; ++it)
-                for (int t = 0; t < nt; ++t) contact_solve_velocity(t);
+                for_contacts(nt, [&](float* hc, const int st, int) { contact_solve_velocity(hc, st); });
             count_contact_solves(nt, vit);
             {
                 V2 v = mk(HB(HB_VX, mb), HB(HB_VY, mb)); float w = HB(HB_W, mb);

@@ -156,6 +156,9 @@ int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_tic
 /* Device time of the kernels launched by the last rem2d_step / rem2d_evaluate, in milliseconds,
  * measured with CUDA events on cfg.stream (0 for the oracle: use wall clock). */
 float rem2d_last_step_ms(rem2d_handle* h);
+/* CUDA build only: measured non-fused FP32 (FMUL/FADD) issue peak of the device in GFLOP/s — the roofline
+ * denominator of the step kernel, which is built without FMA contraction for bit parity with Box2D. */
+int rem2d_measure_fp32_peak(rem2d_handle* h, double* gflops);
 /* Number of kernels this library launched since rem2d_create. */
 int64_t rem2d_launch_count(rem2d_handle* h);
 

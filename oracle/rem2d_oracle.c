@@ -2151,5 +2151,6 @@ int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_tic
     if (ticks_out) for (int c = 0; c < h->n_worlds; ++c) ticks_out[c] = h->worlds[c].ticks;
     return REM2D_OK;
 }
+int rem2d_measure_fp32_peak(rem2d_handle* h, double* gflops) { (void)h; if (gflops) *gflops = 0.0; return REM2D_E_INVALID; }
 float rem2d_last_step_ms(rem2d_handle* h) { (void)h; return 0.0f; }
 int64_t rem2d_launch_count(rem2d_handle* h) { (void)h; return 0; }
