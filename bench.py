@@ -170,12 +170,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # -- device-resident measurement ("value"): table already in HBM, timed region = reset + step + fitness gather
+    # -- device-resident measurement ("value"): population table already in HBM, timed region = rem2d_run_episodes
     eng.upload(pop)
     fit_all = None
     for _ in range(args.warmup):
-        eng.reset()
-        eng.step(K.EVALUATION_STEPS)
+        eng.run_episodes(K.EVALUATION_STEPS)
     barrier()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -183,14 +182,13 @@ def main():
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
-            eng.reset()
-            eng.step(K.EVALUATION_STEPS)
+            eng.run_episodes(K.EVALUATION_STEPS)       # world build + whole episodes, all on the device
             kernel_ms += eng.last_step_ms()
         ev1.record(stream)
         barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - l0
-    counters = eng.counters()          # of the last reset..step
+    counters = eng.counters()          # of the last evaluation
     fit = eng.fitness()
     creature_steps = counters["ticks"]
     t = torch.tensor([ms_total, float(creature_steps)], dtype=torch.float64, device=dev)

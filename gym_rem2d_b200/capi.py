@@ -76,6 +76,8 @@ def load_library(path=None):
     lib.rem2d_fitness.argtypes = [H, C.c_void_p]
     lib.rem2d_get_counters.argtypes = [H, C.c_void_p]
     lib.rem2d_evaluate.argtypes = [H, C.POINTER(Population), C.c_int32, C.c_void_p, C.c_void_p]
+    lib.rem2d_run_episodes.argtypes = [H, C.c_int32]
+    lib.rem2d_ticks.argtypes = [H, C.c_void_p]
     lib.rem2d_last_step_ms.argtypes = [H]
     lib.rem2d_last_step_ms.restype = C.c_float
     lib.rem2d_measure_fp32_peak.argtypes = [H, C.POINTER(C.c_double)]
@@ -161,6 +163,15 @@ class Engine:
 
     def step(self, n_ticks=1):
         self._check(self.lib.rem2d_step(self.h, int(n_ticks)), "rem2d_step")
+
+    def run_episodes(self, max_ticks):
+        """Whole episodes of the uploaded population from tick 0 (persistent episode kernel on the GPU)."""
+        self._check(self.lib.rem2d_run_episodes(self.h, int(max_ticks)), "rem2d_run_episodes")
+
+    def ticks(self):
+        out = np.zeros(self.pop.n_creatures, np.int32)
+        self._check(self.lib.rem2d_ticks(self.h, _ptr(out)), "rem2d_ticks")
+        return out
 
     def fitness(self):
         out = np.zeros(self.pop.n_creatures, np.float64)

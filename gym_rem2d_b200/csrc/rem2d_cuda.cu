@@ -19,16 +19,16 @@ using namespace rem2d;
 // ------------------------------------------------------------------ capacity classes
 // NB bodies, NC contact-pool slots (fat-AABB overlaps), NT touching contacts staged in shared memory
 // (further touching contacts, up to NC, spill to the cold block: correct but slower).
-// hot words/lane = 5*NB + 18*(NB-1) + 21*NT; one warp needs 128 B per word.
+// hot words/lane = 5*NB + 19*(NB-1) + 21*NT; one warp needs 128 B per word.
 #define REM2D_CLASSES(X) \
     X(0, 2, 16, 4)       \
-    X(1, 4, 28, 6)       \
-    X(2, 8, 48, 10)      \
-    X(3, 12, 64, 12)     \
-    X(4, 16, 80, 16)     \
-    X(5, 22, 104, 20)    \
-    X(6, 32, 144, 28)    \
-    X(7, 44, 192, 34)
+    X(1, 4, 28, 4)       \
+    X(2, 8, 48, 6)       \
+    X(3, 12, 64, 6)      \
+    X(4, 16, 80, 8)      \
+    X(5, 22, 104, 8)     \
+    X(6, 32, 144, 10)    \
+    X(7, 44, 192, 12)
 #define N_CLASSES 8
 
 struct ClassInfo { int nb, nc, nt, nj, off_body, off_joint, off_cont, off_edge, words, hot_words; };
@@ -39,94 +39,58 @@ static const ClassInfo g_classes[N_CLASSES] = {
 #undef X
 };
 
-struct DevPop {     // device copy of the flattened table (+ island joint order)
-    const int32_t* body_off; const uint8_t* shape; const float *hx, *hy, *x0, *y0, *a0;
-    const int16_t* joint_parent; const float *anchor_a, *anchor_b, *lower, *upper, *max_torque;
-    const double* ctrl; const uint8_t* joint_order;
-};
-
-// ------------------------------------------------------------------ kernels
-// Build the world of every creature of this class: b2Body/b2Fixture creation (mass data, sweep, proxy fat
-// AABB), joints, controllers, episode scalars. Mirrors oracle world_build()/body_init().
+// Build the world of every creature of this class (static creature -> lane mapping, used by rem2d_step).
 template <int NB, int NC, int NT>
 __global__ void __launch_bounds__(32) reset_kernel(float* state, const int* __restrict__ lane_creature, DevPop p) {
     using SimT = Sim<NB, NC, NT>;
     const int lane = threadIdx.x, batch = blockIdx.x;
     SimT sim;
     sim.g = state + (size_t)batch * SimT::WORDS * 32 + lane;
-    const int c = lane_creature[batch * 32 + lane];
-    for (int w = 0; w < S_COUNT; ++w) sim.g[w * 32] = 0.0f;
-    if (c < 0) { sim.setSi(S_NB, 0); sim.setSi(S_ALIVE, 0); return; }
-    const int b0 = p.body_off[c], nb = p.body_off[c + 1] - b0, nj = nb - 1, j0 = b0 - c;
-    sim.nb = nb; sim.nj = nj;
-    sim.setSi(S_NB, nb); sim.setSi(S_NC, 0); sim.setSi(S_ALIVE, 1); sim.setSi(S_TICKS, 0);
-    sim.setSd(S_WOD_LO, 0.0); sim.setSd(S_FIT_LO, 0.0);
-    sim.S(S_INVDT0) = 0.0f; sim.setSi(S_NEWFIX, 1); sim.setSi(S_STATUS, 0); sim.setSi(S_NADV, 0);
-    for (int e = 0; e < RB_MAX_EDGES; ++e) sim.EA(e) = 0.0f;
-    for (int i = 0; i < nb; ++i) {
-        const int shape = p.shape[b0 + i];
-        const float hx = p.hx[b0 + i], hy = p.hy[b0 + i];
-        const float density = 1.0f;
-        float mass, I;
-        V2 center;
-        if (shape == REM2D_SHAPE_CIRCLE) {
-            mass = density * RB_PI * hx * hx;
-            center = mk(0.0f, 0.0f);
-            I = mass * (0.5f * hx * hx + dot(center, center));
-        } else {
-            V2 v[4] = { mk(-hx, -hy), mk(hx, -hy), mk(hx, hy), mk(-hx, hy) };
-            V2 cen = mk(0.0f, 0.0f), s = mk(0.0f, 0.0f);
-            float area = 0.0f, II = 0.0f;
-            for (int q = 0; q < 4; ++q) s = s + v[q];
-            s = (1.0f / 4.0f) * s;
-            const float k_inv3 = 1.0f / 3.0f;
-            for (int q = 0; q < 4; ++q) {
-                V2 e1 = v[q] - s, e2 = q + 1 < 4 ? v[q + 1] - s : v[0] - s;
-                float D = cross(e1, e2);
-                float triangleArea = 0.5f * D;
-                area += triangleArea;
-                cen = cen + (triangleArea * k_inv3) * (e1 + e2);
-                float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
-                float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
-                II += (0.25f * k_inv3 * D) * (intx2 + inty2);
-            }
-            mass = density * area;
-            cen = (1.0f / area) * cen;
-            center = cen + s;
-            I = density * II;
-            I += mass * (dot(center, center) - dot(cen, cen));
+    sim.build_world(p, lane_creature[batch * 32 + lane]);
+}
+
+// Whole episodes with dynamic lane refill: every lane pulls the next creature of its class from a queue
+// (big creatures first), builds its world in the lane's column of the warp's state block, ticks it until the
+// episode ends, writes fitness / ticks and pulls the next one. Lanes of a warp are therefore always busy until
+// the queue drains, instead of idling until the longest-lived creature of a fixed batch dies; and the cold
+// state of the few hundred resident warps stays L2-resident.
+template <int NB, int NC, int NT>
+__global__ void __launch_bounds__(32) episode_kernel(float* slots, const int* __restrict__ order, int n_order, int* queue,
+                                                     DevPop p, const Terrain* __restrict__ ter, const Consts* __restrict__ k,
+                                                     int max_ticks, double* fitness, int* ticks, int* alive, int* status,
+                                                     unsigned long long* counters) {
+    using SimT = Sim<NB, NC, NT>;
+    extern __shared__ float hot[];
+    const int lane = threadIdx.x;
+    SimT sim;
+    sim.g = slots + (size_t)blockIdx.x * SimT::WORDS * 32 + lane;
+    sim.h = hot + lane;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    int my = -1;
+    bool exhausted = false;
+    for (;;) {
+        if (my < 0 && !exhausted) {
+            int idx = atomicAdd(queue, 1);
+            if (idx < n_order) { my = order[idx]; sim.build_world(p, my); }
+            else exhausted = true;
         }
-        float invMass, invI;
-        V2 localCenter = mass * center;
-        if (mass > 0.0f) { invMass = 1.0f / mass; localCenter = invMass * localCenter; }
-        else { mass = 1.0f; invMass = 1.0f; }
-        if (I > 0.0f) { I -= mass * dot(localCenter, localCenter); invI = 1.0f / I; }
-        else { invI = 0.0f; }
-        const float x = p.x0[b0 + i], y = p.y0[b0 + i], a = p.a0[b0 + i];
-        Rot q = rot_set(a);
-        V2 cpos = xmul(mk(x, y), q, localCenter);          // localCenter == 0 for boxes and circles
-        sim.B(BF_CX, i) = cpos.x; sim.B(BF_CY, i) = cpos.y; sim.B(BF_A, i) = a;
-        sim.B(BF_C0X, i) = cpos.x; sim.B(BF_C0Y, i) = cpos.y; sim.B(BF_A0, i) = a; sim.B(BF_ALPHA0, i) = 0.0f;
-        sim.B(BF_VX, i) = 0.0f; sim.B(BF_VY, i) = 0.0f; sim.B(BF_W, i) = 0.0f;
-        sim.B(BF_QS, i) = q.s; sim.B(BF_QC, i) = q.c;
-        sim.B(BF_SLEEP, i) = 0.0f; sim.B(BF_INVM, i) = invMass; sim.B(BF_INVI, i) = invI;
-        sim.B(BF_HX, i) = hx; sim.B(BF_HY, i) = hy;
-        sim.setBi(BF_FLAGS, i, BFL_AWAKE | BFL_MOVED | (shape == REM2D_SHAPE_CIRCLE ? BFL_CIRCLE : 0));
-        V2 lo, hi;
-        sim.shape_aabb(i, mk(x, y), q, lo, hi);
-        sim.B(BF_FLX, i) = lo.x - RB_AABB_EXT; sim.B(BF_FLY, i) = lo.y - RB_AABB_EXT;
-        sim.B(BF_FHX, i) = hi.x + RB_AABB_EXT; sim.B(BF_FHY, i) = hi.y + RB_AABB_EXT;
+        if (!__any_sync(0xffffffffu, my >= 0)) break;
+        if (my >= 0) {
+            sim.tick();
+            const int t = sim.Si(S_TICKS);
+            if (!sim.Si(S_ALIVE) || t >= max_ticks) {
+                fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = sim.Si(S_STATUS);
+                my = -1;
+            }
+        }
     }
-    for (int j = 0; j < nj; ++j) {
-        sim.setJi(JF_META, j, (int)p.joint_parent[j0 + j] | ((int)p.joint_order[j0 + j] << 8));
-        sim.J(JF_LAAX, j) = p.anchor_a[2 * (j0 + j)]; sim.J(JF_LAAY, j) = p.anchor_a[2 * (j0 + j) + 1];
-        sim.J(JF_LABX, j) = p.anchor_b[2 * (j0 + j)]; sim.J(JF_LABY, j) = p.anchor_b[2 * (j0 + j) + 1];
-        sim.J(JF_IMPX, j) = 0.0f; sim.J(JF_IMPY, j) = 0.0f; sim.J(JF_IMPZ, j) = 0.0f; sim.J(JF_MIMP, j) = 0.0f;
-        sim.J(JF_MSPEED, j) = 0.0f; sim.setJi(JF_LIMIT, j, 0);
-        sim.J(JF_LOWER, j) = p.lower[j0 + j]; sim.J(JF_UPPER, j) = p.upper[j0 + j]; sim.J(JF_MAXT, j) = p.max_torque[j0 + j];
-        const double* cc = &p.ctrl[(size_t)(b0 + j + 1) * 5];     // controller of body j+1 drives joint j
-        sim.setJd(JF_AMP, j, cc[0]); sim.setJd(JF_PHASE, j, cc[1]); sim.setJd(JF_FREQ, j, cc[2]);
-        sim.setJd(JF_OFFS, j, cc[3]); sim.setJd(JF_ISTATE, j, cc[4]);
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
+        unsigned long long v = sim.cnt.c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&counters[i], v);
     }
 }
 
@@ -187,8 +151,11 @@ __global__ void fp32_issue_kernel(float* out, int iters, float b, float c) {
 struct ClassState {
     std::vector<int> lane_creature;     // host copy: [n_batches*32], -1 = padding lane
     int n_batches = 0;
+    int n_members = 0;                  // creatures of this class (lane_creature[0..n_members) are real)
+    int episode_grid = 0;               // resident warps of the persistent episode kernel
     float* d_state = nullptr;
     int* d_lane_creature = nullptr;
+    int* d_queue = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
 };
@@ -200,6 +167,9 @@ struct rem2d_handle {
     Consts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;
     bool have_terrain = false, have_pop = false;
+    bool state_valid = false;           // per-creature state blocks hold a consistent snapshot (reset/step path)
+    bool results_valid = false;         // d_fitness/d_ticks/... were written by the episode kernel
+    int n_sms = 0;
     int n_edges = 0;
     // population
     int n_creatures = 0, n_bodies = 0, n_joints = 0;
@@ -232,14 +202,15 @@ static void free_population(rem2d_handle* h) {
     for (auto& c : h->cls) {
         if (c.d_state) cudaFree(c.d_state);
         if (c.d_lane_creature) cudaFree(c.d_lane_creature);
-        c.d_state = nullptr; c.d_lane_creature = nullptr; c.n_batches = 0; c.lane_creature.clear();
+        if (c.d_queue) cudaFree(c.d_queue);
+        c.d_state = nullptr; c.d_lane_creature = nullptr; c.d_queue = nullptr; c.n_batches = 0; c.n_members = 0; c.lane_creature.clear();
     }
     if (h->d_fitness) cudaFree(h->d_fitness);
     if (h->d_ticks) cudaFree(h->d_ticks);
     if (h->d_alive) cudaFree(h->d_alive);
     if (h->d_status) cudaFree(h->d_status);
     h->d_fitness = nullptr; h->d_ticks = h->d_alive = h->d_status = nullptr;
-    h->have_pop = false;
+    h->have_pop = false; h->state_valid = false; h->results_valid = false;
 }
 
 extern "C" {
@@ -300,8 +271,11 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
     }
     cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device);
 #define X(i, NB, NC, NT)                                                                                              \
     if ((e = cudaFuncSetAttribute(step_kernel<NB, NC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                  Sim<NB, NC, NT>::HOT_WORDS * 128)) != cudaSuccess) return fail("cudaFuncSetAttribute", e); \
+    if ((e = cudaFuncSetAttribute(episode_kernel<NB, NC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                   Sim<NB, NC, NT>::HOT_WORDS * 128)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
     REM2D_CLASSES(X)
 #undef X
@@ -394,7 +368,7 @@ static cudaError_t upload_array(rem2d_handle* h, int slot, const T* src, size_t 
 
 static int launch_reset(rem2d_handle* h);
 
-extern "C" int rem2d_upload(rem2d_handle* h, const rem2d_population* pop) {
+static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_reset) {
     if (!h || !pop) return REM2D_E_INVALID;
     if (pop->n_creatures < 0 || pop->n_joints != pop->n_bodies - pop->n_creatures) { h->err = "upload: inconsistent counts"; return REM2D_E_INVALID; }
     cudaSetDevice(h->cfg.device);
@@ -450,6 +424,12 @@ extern "C" int rem2d_upload(rem2d_handle* h, const rem2d_population* pop) {
         });
         ClassState& cs = h->cls[k];
         cs.n_batches = (int)((m.size() + 31) / 32);
+        cs.n_members = (int)m.size();
+        {   // resident warps of the episode kernel: as many as fit next to each other on the SMs (227 KB shared memory each)
+            int per_sm = std::max(1, std::min(32, (227 * 1024) / (g_classes[k].hot_words * 128 + 1024)));
+            cs.episode_grid = std::min(cs.n_batches, h->n_sms * per_sm);
+        }
+        CK(cudaMalloc(&cs.d_queue, sizeof(int)));
         cs.lane_creature.assign((size_t)cs.n_batches * 32, -1);
         for (size_t i = 0; i < m.size(); ++i) { cs.lane_creature[i] = m[i]; h->creature_lane[m[i]] = (int)i; }
         CK(cudaMalloc(&cs.d_lane_creature, cs.lane_creature.size() * sizeof(int)));
@@ -462,8 +442,10 @@ extern "C" int rem2d_upload(rem2d_handle* h, const rem2d_population* pop) {
     CK(cudaMalloc(&h->d_status, sizeof(int) * std::max(n, 1)));
     h->h_fitness.assign(n, 0.0); h->h_ticks.assign(n, 0); h->h_alive.assign(n, 0); h->h_status.assign(n, 0);
     h->have_pop = true;
-    return launch_reset(h);
+    return do_reset ? launch_reset(h) : REM2D_OK;
 }
+
+extern "C" int rem2d_upload(rem2d_handle* h, const rem2d_population* pop) { return upload_impl(h, pop, true); }
 
 // fork the class streams off the user stream / join them back
 static int fork_streams(rem2d_handle* h) {
@@ -494,6 +476,38 @@ static int launch_reset(rem2d_handle* h) {
     rc = join_streams(h);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
+    h->state_valid = true; h->results_valid = false;
+    return REM2D_OK;
+}
+
+// Whole episodes for the uploaded population on the persistent episode kernels (one per class, concurrent).
+static int launch_episodes(rem2d_handle* h, int max_ticks) {
+    if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
+    CK(cudaEventRecord(h->ev_start, h->user_stream));
+    int rc = fork_streams(h);
+    if (rc) return rc;
+    for (int k = N_CLASSES - 1; k >= 0; --k) {
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches) continue;
+        CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
+        switch (k) {
+#define X(i, NB, NC, NT)                                                                                             \
+    case i:                                                                                                          \
+        episode_kernel<NB, NC, NT><<<cs.episode_grid, 32, Sim<NB, NC, NT>::HOT_WORDS * 128, cs.stream>>>(           \
+            cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter, h->d_consts, max_ticks,     \
+            h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);                                       \
+        break;
+            REM2D_CLASSES(X)
+#undef X
+        }
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    rc = join_streams(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_stop, h->user_stream));
+    h->state_valid = false; h->results_valid = true;
     return REM2D_OK;
 }
 
@@ -505,7 +519,8 @@ extern "C" int rem2d_reset(rem2d_handle* h) {
 }
 
 static int gather(rem2d_handle* h) {
-    for (int k = 0; k < N_CLASSES; ++k) {
+    if (!h->state_valid && !h->results_valid) { h->err = "no results: call rem2d_reset/rem2d_step or rem2d_run_episodes first"; return REM2D_E_INVALID; }
+    for (int k = 0; k < N_CLASSES && h->state_valid; ++k) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
         int n_lanes = cs.n_batches * 32;
@@ -535,6 +550,7 @@ extern "C" {
 int rem2d_step(rem2d_handle* h, int32_t n_ticks) {
     if (!h) return REM2D_E_INVALID;
     if (!h->have_pop || n_ticks < 0) { h->err = "step: no population / negative tick count"; return REM2D_E_INVALID; }
+    if (!h->state_valid) { h->err = "step: per-creature state was consumed by rem2d_run_episodes/rem2d_evaluate; call rem2d_reset first"; return REM2D_E_INVALID; }
     cudaSetDevice(h->cfg.device);
     CK(cudaEventRecord(h->ev_start, h->user_stream));
     int rc = fork_streams(h);
@@ -580,10 +596,31 @@ int rem2d_get_counters(rem2d_handle* h, uint64_t* out) {
     return REM2D_OK;
 }
 
-int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_ticks, double* fitness_out, int32_t* ticks_out) {
-    int rc = rem2d_upload(h, pop);
+int rem2d_run_episodes(rem2d_handle* h, int32_t max_ticks) {
+    if (!h) return REM2D_E_INVALID;
+    if (!h->have_pop || max_ticks < 0) { h->err = "run_episodes: no population / negative tick count"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    int rc = launch_episodes(h, max_ticks);
     if (rc) return rc;
-    rc = rem2d_step(h, max_ticks);
+    CK(cudaEventSynchronize(h->ev_stop));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev_start, h->ev_stop));
+    return REM2D_OK;
+}
+
+int rem2d_ticks(rem2d_handle* h, int32_t* out) {
+    if (!h || !out) return REM2D_E_INVALID;
+    if (!h->have_pop) { h->err = "ticks: no population uploaded"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    int rc = gather(h);
+    if (rc) return rc;
+    memcpy(out, h->h_ticks.data(), sizeof(int) * h->n_creatures);
+    return REM2D_OK;
+}
+
+int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_ticks, double* fitness_out, int32_t* ticks_out) {
+    int rc = upload_impl(h, pop, false);      // the episode kernel builds the worlds itself
+    if (rc) return rc;
+    rc = rem2d_run_episodes(h, max_ticks);
     if (rc) return rc;
     rc = gather(h);
     if (rc) return rc;
@@ -624,6 +661,7 @@ int64_t rem2d_launch_count(rem2d_handle* h) { return h ? h->launches : 0; }
 int rem2d_read_state(rem2d_handle* h, rem2d_state_view* out) {
     if (!h || !out) return REM2D_E_INVALID;
     if (!h->have_pop) { h->err = "read_state: no population uploaded"; return REM2D_E_INVALID; }
+    if (!h->state_valid) { h->err = "read_state: per-creature state was consumed by rem2d_run_episodes; call rem2d_reset first"; return REM2D_E_INVALID; }
     cudaSetDevice(h->cfg.device);
     CK(cudaStreamSynchronize(h->user_stream));
     for (int k = 0; k < N_CLASSES; ++k) {

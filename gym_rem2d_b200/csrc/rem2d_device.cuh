@@ -145,10 +145,10 @@ enum { CF_KEY, CF_TOI, CF_LNX, CF_LNY, CF_LPX, CF_LPY, CF_P0X, CF_P0Y, CF_P0N, C
 #define ST_POOL_OVERFLOW 1     // contact pool (NC) exhausted
 #define ST_TOI_OVERFLOW 4      // TOI mini-island larger than RB_TOI_ISLAND_CAP
 
-// hot (shared memory) layout, words per lane: 5*NB + 18*NJ + 21*NT
+// hot (shared memory) layout, words per lane: 5*NB + 19*NJ + 21*NT
 enum { HB_VX, HB_VY, HB_W, HB_INVM, HB_INVI, HB_COUNT };                 // position phase: CX, CY, A reuse 0..2
-enum { HJ_META, HJ_RAX, HJ_RAY, HJ_RBX, HJ_RBY, HJ_EXX, HJ_EYX, HJ_EZX, HJ_EYY, HJ_EZY, HJ_EZZ, HJ_MMASS,
-       HJ_IMPX, HJ_IMPY, HJ_IMPZ, HJ_MIMP, HJ_MSPEED, HJ_MAXIMP, HJ_COUNT };
+enum { HJ_META, HJ_RAX, HJ_RAY, HJ_RBX, HJ_RBY, HJ_EXX, HJ_EYX, HJ_EZX, HJ_EYY, HJ_EZY, HJ_INV2, HJ_INV3, HJ_MMASS,
+       HJ_IMPX, HJ_IMPY, HJ_IMPZ, HJ_MIMP, HJ_MSPEED, HJ_MAXIMP, HJ_COUNT };   // INV2/INV3: 1/det of the 2x2 / 3x3 blocks
 // position-phase overlay of a joint slot
 enum { PJ_META = HJ_META, PJ_LAAX, PJ_LAAY, PJ_LABX, PJ_LABY, PJ_LOWER, PJ_UPPER };
 enum { HC_META, HC_NX, HC_NY, HC_R0X, HC_R0Y, HC_NM0, HC_TM0, HC_NI0, HC_TI0, HC_R1X, HC_R1Y, HC_NM1, HC_TM1,
@@ -169,6 +169,12 @@ struct Consts {
     double p_gain, wod_speed, env_length;
 };
 
+// device copy of the flattened population table (+ island joint order)
+struct DevPop {
+    const int32_t* body_off; const uint8_t* shape; const float *hx, *hy, *x0, *y0, *a0;
+    const int16_t* joint_parent; const float *anchor_a, *anchor_b, *lower, *upper, *max_torque;
+    const double* ctrl; const uint8_t* joint_order;
+};
 // work counters kept in registers and flushed once per launch
 struct Cnt { unsigned int c[REM2D_N_COUNTERS]; };   // per lane per launch; summed into 64-bit totals
 
@@ -294,6 +300,85 @@ struct Sim {
         if (d1x > 0.0f || d1y > 0.0f) return false;
         if (d2x > 0.0f || d2y > 0.0f) return false;
         return true;
+    }
+
+
+    // ---- world construction: b2Body/b2Fixture creation (mass data, sweep, proxy fat AABB), joints, controllers and
+    // episode scalars of creature c (c < 0: empty lane). Mirrors oracle world_build()/body_init().
+    __device__ void build_world(const DevPop& p, int c) {
+        for (int w = 0; w < S_COUNT; ++w) g[w * 32] = 0.0f;
+        if (c < 0) { nb = 0; nj = 0; setSi(S_NB, 0); setSi(S_ALIVE, 0); return; }
+        const int b0 = p.body_off[c], j0 = b0 - c;
+        nb = p.body_off[c + 1] - b0; nj = nb - 1;
+        setSi(S_NB, nb); setSi(S_NC, 0); setSi(S_ALIVE, 1); setSi(S_TICKS, 0);
+        setSd(S_WOD_LO, 0.0); setSd(S_FIT_LO, 0.0);
+        S(S_INVDT0) = 0.0f; setSi(S_NEWFIX, 1); setSi(S_STATUS, 0); setSi(S_NADV, 0);
+        for (int e = 0; e < RB_MAX_EDGES; ++e) EA(e) = 0.0f;
+        for (int i = 0; i < nb; ++i) {
+            const int shape = p.shape[b0 + i];
+            const float hx = p.hx[b0 + i], hy = p.hy[b0 + i];
+            const float density = 1.0f;
+            float mass, I;
+            V2 center;
+            if (shape == REM2D_SHAPE_CIRCLE) {
+                mass = density * RB_PI * hx * hx;
+                center = mk(0.0f, 0.0f);
+                I = mass * (0.5f * hx * hx + dot(center, center));
+            } else {
+                V2 v[4] = { mk(-hx, -hy), mk(hx, -hy), mk(hx, hy), mk(-hx, hy) };
+                V2 cen = mk(0.0f, 0.0f), s = mk(0.0f, 0.0f);
+                float area = 0.0f, II = 0.0f;
+                for (int q = 0; q < 4; ++q) s = s + v[q];
+                s = (1.0f / 4.0f) * s;
+                const float k_inv3 = 1.0f / 3.0f;
+                for (int q = 0; q < 4; ++q) {
+                    V2 e1 = v[q] - s, e2 = q + 1 < 4 ? v[q + 1] - s : v[0] - s;
+                    float D = cross(e1, e2);
+                    float triangleArea = 0.5f * D;
+                    area += triangleArea;
+                    cen = cen + (triangleArea * k_inv3) * (e1 + e2);
+                    float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
+                    float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
+                    II += (0.25f * k_inv3 * D) * (intx2 + inty2);
+                }
+                mass = density * area;
+                cen = (1.0f / area) * cen;
+                center = cen + s;
+                I = density * II;
+                I += mass * (dot(center, center) - dot(cen, cen));
+            }
+            float invMass, invI;
+            V2 localCenter = mass * center;
+            if (mass > 0.0f) { invMass = 1.0f / mass; localCenter = invMass * localCenter; }
+            else { mass = 1.0f; invMass = 1.0f; }
+            if (I > 0.0f) { I -= mass * dot(localCenter, localCenter); invI = 1.0f / I; }
+            else { invI = 0.0f; }
+            const float x = p.x0[b0 + i], y = p.y0[b0 + i], a = p.a0[b0 + i];
+            Rot q = rot_set(a);
+            V2 cpos = xmul(mk(x, y), q, localCenter);          // localCenter == 0 for boxes and circles
+            B(BF_CX, i) = cpos.x; B(BF_CY, i) = cpos.y; B(BF_A, i) = a;
+            B(BF_C0X, i) = cpos.x; B(BF_C0Y, i) = cpos.y; B(BF_A0, i) = a; B(BF_ALPHA0, i) = 0.0f;
+            B(BF_VX, i) = 0.0f; B(BF_VY, i) = 0.0f; B(BF_W, i) = 0.0f;
+            B(BF_QS, i) = q.s; B(BF_QC, i) = q.c;
+            B(BF_SLEEP, i) = 0.0f; B(BF_INVM, i) = invMass; B(BF_INVI, i) = invI;
+            B(BF_HX, i) = hx; B(BF_HY, i) = hy;
+            setBi(BF_FLAGS, i, BFL_AWAKE | BFL_MOVED | (shape == REM2D_SHAPE_CIRCLE ? BFL_CIRCLE : 0));
+            V2 lo, hi;
+            shape_aabb(i, mk(x, y), q, lo, hi);
+            B(BF_FLX, i) = lo.x - RB_AABB_EXT; B(BF_FLY, i) = lo.y - RB_AABB_EXT;
+            B(BF_FHX, i) = hi.x + RB_AABB_EXT; B(BF_FHY, i) = hi.y + RB_AABB_EXT;
+        }
+        for (int j = 0; j < nj; ++j) {
+            setJi(JF_META, j, (int)p.joint_parent[j0 + j] | ((int)p.joint_order[j0 + j] << 8));
+            J(JF_LAAX, j) = p.anchor_a[2 * (j0 + j)]; J(JF_LAAY, j) = p.anchor_a[2 * (j0 + j) + 1];
+            J(JF_LABX, j) = p.anchor_b[2 * (j0 + j)]; J(JF_LABY, j) = p.anchor_b[2 * (j0 + j) + 1];
+            J(JF_IMPX, j) = 0.0f; J(JF_IMPY, j) = 0.0f; J(JF_IMPZ, j) = 0.0f; J(JF_MIMP, j) = 0.0f;
+            J(JF_MSPEED, j) = 0.0f; setJi(JF_LIMIT, j, 0);
+            J(JF_LOWER, j) = p.lower[j0 + j]; J(JF_UPPER, j) = p.upper[j0 + j]; J(JF_MAXT, j) = p.max_torque[j0 + j];
+            const double* cc = &p.ctrl[(size_t)(b0 + j + 1) * 5];     // controller of body j+1 drives joint j
+            setJd(JF_AMP, j, cc[0]); setJd(JF_PHASE, j, cc[1]); setJd(JF_FREQ, j, cc[2]);
+            setJd(JF_OFFS, j, cc[3]); setJd(JF_ISTATE, j, cc[4]);
+        }
     }
 
     // ---- contact pool (creation order; index nc-1 is the newest == head of Box2D's lists)
@@ -742,15 +827,17 @@ struct Sim {
             impulse = ni - oldImpulse;
             wA -= iA * impulse; wB += iB * impulse;
         }
+        // The effective-mass matrix is constant over the 180 iterations, so the reciprocal determinants that
+        // b2Mat33::Solve33 / Solve22 recompute on every call are taken from the slot (same value, same bits).
         float exx = HJ(HJ_EXX, s), eyx = HJ(HJ_EYX, s), eyy = HJ(HJ_EYY, s);
+        const float d2 = HJ(HJ_INV2, s);
         if (limit != 0) {
-            float ezx = HJ(HJ_EZX, s), ezy = HJ(HJ_EZY, s), ezz = HJ(HJ_EZZ, s);
+            float ezx = HJ(HJ_EZX, s), ezy = HJ(HJ_EZY, s), ezz = iA + iB;
             V2 Cdot1 = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
             float Cdot2 = wB - wA;
             // Solve33: ex = (exx, eyx, ezx), ey = (eyx, eyy, ezy), ez = (ezx, ezy, ezz)
             float cx = eyy * ezz - ezy * ezy, cy = ezy * ezx - eyx * ezz, cz = eyx * ezy - eyy * ezx;   // ey x ez
-            float det = exx * cx + eyx * cy + ezx * cz;
-            if (det != 0.0f) det = 1.0f / det;
+            const float det = HJ(HJ_INV3, s);
             float ix = det * (Cdot1.x * cx + Cdot1.y * cy + Cdot2 * cz);
             // b x ez
             float bx = Cdot1.y * ezz - Cdot2 * ezy, by = Cdot2 * ezx - Cdot1.x * ezz, bz = Cdot1.x * ezy - Cdot1.y * ezx;
@@ -764,8 +851,6 @@ struct Sim {
             bool reduce = (limit == 1) ? (newImpulse < 0.0f) : (newImpulse > 0.0f);
             if (reduce) {
                 V2 rhs = -Cdot1 + jz * mk(ezx, ezy);
-                float d2 = exx * eyy - eyx * eyx;
-                if (d2 != 0.0f) d2 = 1.0f / d2;
                 float rx = d2 * (eyy * rhs.x - eyx * rhs.y), ry = d2 * (exx * rhs.y - eyx * rhs.x);
                 ix = rx; iy = ry; iz = -jz;
                 HJ(HJ_IMPX, s) += rx; HJ(HJ_IMPY, s) += ry; HJ(HJ_IMPZ, s) = 0.0f;
@@ -778,8 +863,6 @@ struct Sim {
         } else {
             V2 Cdot = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
             V2 nb_ = -Cdot;
-            float d2 = exx * eyy - eyx * eyx;
-            if (d2 != 0.0f) d2 = 1.0f / d2;
             V2 imp = mk(d2 * (eyy * nb_.x - eyx * nb_.y), d2 * (exx * nb_.y - eyx * nb_.x));
             HJ(HJ_IMPX, s) += imp.x; HJ(HJ_IMPY, s) += imp.y;
             vA = vA - mA * imp; wA -= iA * cross(rA, imp);
@@ -922,7 +1005,15 @@ struct Sim {
             HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
             HJ(HJ_META, s) = __int_as_float(a | (b << 8) | (limit << 16) | (j << 24));
             HJ(HJ_RAX, s) = rA.x; HJ(HJ_RAY, s) = rA.y; HJ(HJ_RBX, s) = rB.x; HJ(HJ_RBY, s) = rB.y;
-            HJ(HJ_EXX, s) = exx; HJ(HJ_EYX, s) = eyx; HJ(HJ_EZX, s) = ezx; HJ(HJ_EYY, s) = eyy; HJ(HJ_EZY, s) = ezy; HJ(HJ_EZZ, s) = ezz;
+            HJ(HJ_EXX, s) = exx; HJ(HJ_EYX, s) = eyx; HJ(HJ_EZX, s) = ezx; HJ(HJ_EYY, s) = eyy; HJ(HJ_EZY, s) = ezy;
+            {
+                float inv2 = exx * eyy - eyx * eyx;
+                if (inv2 != 0.0f) inv2 = 1.0f / inv2;
+                float cx = eyy * ezz - ezy * ezy, cy = ezy * ezx - eyx * ezz, cz = eyx * ezy - eyy * ezx;
+                float inv3 = exx * cx + eyx * cy + ezx * cz;
+                if (inv3 != 0.0f) inv3 = 1.0f / inv3;
+                HJ(HJ_INV2, s) = inv2; HJ(HJ_INV3, s) = inv3;
+            }
             HJ(HJ_MMASS, s) = motorMass;
             HJ(HJ_IMPX, s) = impx; HJ(HJ_IMPY, s) = impy; HJ(HJ_IMPZ, s) = impz; HJ(HJ_MIMP, s) = mimp;
             HJ(HJ_MSPEED, s) = J(JF_MSPEED, j);

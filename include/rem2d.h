@@ -149,7 +149,12 @@ int rem2d_read_state(rem2d_handle* h, rem2d_state_view* out);
 /* fitness as evaluate() would return it so far (REM2D_main.py:361-378) */
 int rem2d_fitness(rem2d_handle* h, double* out_n_creatures);
 int rem2d_get_counters(rem2d_handle* h, uint64_t* out_REM2D_N_COUNTERS);
-/* Batched evaluate(): upload + reset + step(max_ticks) + fitness; ticks_out may be NULL. This is the
+/* Whole episodes for the uploaded population, from tick 0 to termination (or max_ticks), on the persistent
+ * episode kernel; results via rem2d_fitness / rem2d_ticks. Per-creature stepping state is not kept: call
+ * rem2d_reset before using rem2d_step / rem2d_read_state again. */
+int rem2d_run_episodes(rem2d_handle* h, int32_t max_ticks);
+int rem2d_ticks(rem2d_handle* h, int32_t* out_n_creatures);
+/* Batched evaluate(): upload + run_episodes(max_ticks) + fitness; ticks_out may be NULL. This is the
  * call toolbox.map(toolbox.evaluate, population) (REM2D_main.py:267,291) turns into. */
 int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_ticks,
                    double* fitness_out, int32_t* ticks_out);

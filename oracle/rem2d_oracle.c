@@ -2142,6 +2142,16 @@ int rem2d_get_counters(rem2d_handle* h, uint64_t* out) {
     memcpy(out, h->counters, sizeof(h->counters));
     return REM2D_OK;
 }
+int rem2d_run_episodes(rem2d_handle* h, int32_t max_ticks) {
+    int rc = rem2d_reset(h);
+    if (rc) return rc;
+    return rem2d_step(h, max_ticks);
+}
+int rem2d_ticks(rem2d_handle* h, int32_t* out) {
+    if (!h || !out || !h->have_pop) return REM2D_E_INVALID;
+    for (int c = 0; c < h->n_worlds; ++c) out[c] = h->worlds[c].ticks;
+    return REM2D_OK;
+}
 int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_ticks, double* fitness_out, int32_t* ticks_out) {
     int rc = rem2d_upload(h, pop);
     if (rc) return rc;

@@ -88,3 +88,22 @@ def test_single_body_creatures_sleep_and_die_like_the_oracle():
     for _ in range(5):
         g.step(30); o.step(30)
         assert_same_state(g.read_state(max_pairs=8), o.read_state(max_pairs=8), "single-body")
+
+
+def test_episode_kernel_matches_stepping_kernel():
+    """rem2d_run_episodes (persistent kernel, lanes refilled from a queue) vs reset + step on the same GPU."""
+    random.seed(31)
+    pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(700)])
+    xs, ys = terrain.generate_terrain()
+    g = Engine(device=0)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    g.upload(pop)
+    g.step(K.EVALUATION_STEPS)
+    f1, t1, c1 = g.fitness(), g.ticks(), g.counters()
+    g.run_episodes(K.EVALUATION_STEPS)
+    f2, t2, c2 = g.fitness(), g.ticks(), g.counters()
+    assert np.array_equal(f1, f2) and np.array_equal(t1, t2) and c1 == c2
+    with pytest.raises(Exception):
+        g.step(1)                      # stepping state was consumed by the episode kernel
+    g.reset(); g.step(3)
+    assert (g.read_state()["ticks"] == 3).all()
