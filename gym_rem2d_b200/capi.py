@@ -3,7 +3,7 @@
 The product library is ``csrc/librem2d_cuda.so`` (hand-written CUDA for sm_100a). There is NO CPU
 fallback: if the library is missing, or no CUDA device is usable, loading/creating raises.
 The binding class itself is library-agnostic because the CPU oracle exports the same ABI; only the
-tests point it at ``oracle/librem2d_oracle.so`` (see oracle/oracle.py).
+tests point it at the oracle's shared object (see oracle/oracle.py) — nothing in this package does.
 """
 import ctypes as C
 import os

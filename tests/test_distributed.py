@@ -1,0 +1,68 @@
+"""Multi-rank logic on CPU: world_size 2 over gloo. The shards are evaluated with the oracle here
+(no GPU in this container); on the GPU box the same code path runs with the CUDA engine."""
+import os
+import random
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from gym_rem2d_b200 import Individual, constants as K, terrain
+from gym_rem2d_b200.distributed import shard_indices
+from gym_rem2d_b200.flatten import flatten_population
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, table, ys, ret):
+    import torch.distributed as dist
+    from gym_rem2d_b200.distributed import evaluate_sharded
+    from oracle.oracle import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def make():
+        e = OracleEngine()
+        e.set_terrain(ys, K.TERRAIN_STEP)
+        return e
+    fit, steps = evaluate_sharded(table, make, 400)
+    ret[rank] = (fit, steps)
+    dist.destroy_process_group()
+
+
+def test_shards_partition_population_and_balance_sizes():
+    random.seed(3)
+    table = flatten_population([Individual.random(encoding="lsystem") for _ in range(101)])
+    nb = np.diff(table.body_off)
+    for world in (1, 2, 4, 8):
+        parts = [shard_indices(table.body_off, r, world) for r in range(world)]
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(101))
+        loads = [nb[p].sum() for p in parts]
+        assert max(loads) - min(loads) <= nb.max() + 1
+
+
+def test_two_ranks_gloo_gather_equals_single_rank():
+    random.seed(4)
+    table = flatten_population([Individual.random(encoding="direct") for _ in range(37)])
+    xs, ys = terrain.generate_terrain()
+    from oracle.oracle import OracleEngine
+    e = OracleEngine()
+    e.set_terrain(ys, K.TERRAIN_STEP)
+    ref, ticks = e.evaluate(table, 400)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, table, ys, ret), nprocs=2, join=True)
+    for r in range(2):
+        fit, steps = ret[r]
+        assert np.array_equal(fit, ref.astype(np.float32))      # bitwise identical, any shard count
+    assert ret[0][1] + ret[1][1] == int(ticks.sum())
