@@ -1,0 +1,123 @@
+// rem2d_class.cu — the three kernels of ONE capacity class (compiled once per class with -DREM2D_CLASS_ID=k).
+#include "rem2d_classes.h"
+
+using namespace rem2d;
+
+// Build the world of every creature of this class (static creature -> lane mapping, used by rem2d_step).
+template <int NB, int NC, int NT>
+__global__ void __launch_bounds__(32) reset_kernel(float* state, const int* __restrict__ lane_creature, DevPop p) {
+    using SimT = Sim<NB, NC, NT>;
+    const int lane = threadIdx.x, batch = blockIdx.x;
+    SimT sim;
+    sim.g = state + (size_t)batch * SimT::WORDS * 32 + lane;
+    sim.build_world(p, lane_creature[batch * 32 + lane]);
+}
+
+// Whole episodes with dynamic lane refill: every lane pulls the next creature of its class from a queue
+// (big creatures first), builds its world in the lane's column of the warp's state block, ticks it until the
+// episode ends, writes fitness / ticks and pulls the next one. Lanes of a warp are therefore always busy until
+// the queue drains, instead of idling until the longest-lived creature of a fixed batch dies; and the cold
+// state of the few hundred resident warps stays L2-resident.
+template <int NB, int NC, int NT>
+__global__ void __launch_bounds__(32) episode_kernel(float* slots, const int* __restrict__ order, int n_order, int* queue,
+                                                     DevPop p, const Terrain* __restrict__ ter, const Consts* __restrict__ k,
+                                                     int max_ticks, double* fitness, int* ticks, int* alive, int* status,
+                                                     unsigned long long* counters) {
+    using SimT = Sim<NB, NC, NT>;
+    extern __shared__ float hot[];
+    const int lane = threadIdx.x;
+    SimT sim;
+    sim.g = slots + (size_t)blockIdx.x * SimT::WORDS * 32 + lane;
+    sim.h = hot + lane;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    int my = -1;
+    bool exhausted = false;
+    Cnt snapshot = sim.cnt;
+    for (;;) {
+        if (my < 0 && !exhausted) {
+            int idx = atomicAdd(queue, 1);
+            if (idx < n_order) { my = order[idx]; sim.build_world(p, my); snapshot = sim.cnt; }
+            else exhausted = true;
+        }
+        if (!__any_sync(0xffffffffu, my >= 0)) break;
+        if (my >= 0) {
+            sim.tick();
+            const int t = sim.Si(S_TICKS), st = sim.Si(S_STATUS);
+            if (!sim.Si(S_ALIVE) || t >= max_ticks || st) {
+                fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = st;
+                // a creature that outgrew a capacity of this class is re-run by the host in the next class up:
+                // its partial work must not be counted
+                if (st) sim.cnt = snapshot;
+                my = -1;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
+        unsigned long long v = sim.cnt.c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&counters[i], v);
+    }
+}
+
+// One warp per batch of 32 creatures; each lane advances its creature by up to n_ticks ticks.
+template <int NB, int NC, int NT>
+__global__ void __launch_bounds__(32) step_kernel(float* state, int n_ticks, const Terrain* __restrict__ ter,
+                                                  const Consts* __restrict__ k, unsigned long long* counters) {
+    using SimT = Sim<NB, NC, NT>;
+    extern __shared__ float hot[];
+    const int lane = threadIdx.x, batch = blockIdx.x;
+    SimT sim;
+    sim.g = state + (size_t)batch * SimT::WORDS * 32 + lane;
+    sim.h = hot + lane;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
+    if (sim.nb > 0) {
+        for (int t = 0; t < n_ticks; ++t) {
+            if (!sim.Si(S_ALIVE)) break;
+            sim.tick();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
+        unsigned long long v = sim.cnt.c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&counters[i], v);
+    }
+}
+
+
+#define X(i, NB_, NC_, NT_) \
+    constexpr int kNB_##i = NB_, kNC_##i = NC_, kNT_##i = NT_;
+REM2D_CLASSES(X)
+#undef X
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+constexpr int kNB = CAT(kNB_, REM2D_CLASS_ID), kNC = CAT(kNC_, REM2D_CLASS_ID), kNT = CAT(kNT_, REM2D_CLASS_ID);
+using SimK = Sim<kNB, kNC, kNT>;
+
+static cudaError_t set_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<kNB, kNC, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SimK::HOT_WORDS * 128);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(episode_kernel<kNB, kNC, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SimK::HOT_WORDS * 128);
+}
+static void launch_reset(int grid, cudaStream_t st, float* state, const int* lane_creature, DevPop p) {
+    reset_kernel<kNB, kNC, kNT><<<grid, 32, 0, st>>>(state, lane_creature, p);
+}
+static void launch_step(int grid, cudaStream_t st, float* state, int n_ticks, const Terrain* ter, const Consts* k,
+                        unsigned long long* counters) {
+    step_kernel<kNB, kNC, kNT><<<grid, 32, SimK::HOT_WORDS * 128, st>>>(state, n_ticks, ter, k, counters);
+}
+static void launch_episode(int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue, DevPop p,
+                           const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
+                           unsigned long long* counters) {
+    episode_kernel<kNB, kNC, kNT><<<grid, 32, SimK::HOT_WORDS * 128, st>>>(slots, order, n_order, queue, p, ter, k, max_ticks,
+                                                                            fitness, ticks, alive, status, counters);
+}
+extern const ClassOps CAT(rem2d_class_ops_, REM2D_CLASS_ID) = {
+    kNB, kNC, kNT, SimK::NJ, SimK::OFF_BODY, SimK::OFF_JOINT, SimK::OFF_CONT, SimK::OFF_EDGE, SimK::WORDS, SimK::HOT_WORDS,
+    set_attributes, launch_reset, launch_step, launch_episode };

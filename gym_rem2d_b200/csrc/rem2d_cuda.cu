@@ -12,115 +12,17 @@
 #include <string>
 #include <vector>
 
-#include "rem2d_device.cuh"
+#include "rem2d_classes.h"
 
 using namespace rem2d;
 
-// ------------------------------------------------------------------ capacity classes
-// NB bodies, NC contact-pool slots (fat-AABB overlaps), NT touching contacts staged in shared memory
-// (further touching contacts, up to NC, spill to the cold block: correct but slower).
-// hot words/lane = 5*NB + 19*(NB-1) + 21*NT; one warp needs 128 B per word.
-#define REM2D_CLASSES(X) \
-    X(0, 2, 16, 4)       \
-    X(1, 4, 28, 4)       \
-    X(2, 8, 48, 6)       \
-    X(3, 12, 64, 6)      \
-    X(4, 16, 80, 8)      \
-    X(5, 22, 104, 8)     \
-    X(6, 32, 144, 10)    \
-    X(7, 44, 192, 12)
-#define N_CLASSES 8
-
-struct ClassInfo { int nb, nc, nt, nj, off_body, off_joint, off_cont, off_edge, words, hot_words; };
-static const ClassInfo g_classes[N_CLASSES] = {
-#define X(i, NB, NC, NT) { NB, NC, NT, Sim<NB, NC, NT>::NJ, Sim<NB, NC, NT>::OFF_BODY, Sim<NB, NC, NT>::OFF_JOINT, \
-                           Sim<NB, NC, NT>::OFF_CONT, Sim<NB, NC, NT>::OFF_EDGE, Sim<NB, NC, NT>::WORDS, Sim<NB, NC, NT>::HOT_WORDS },
+// ------------------------------------------------------------------ capacity classes (rem2d_classes.h)
+static const ClassOps* const g_classes_p[N_CLASSES] = {
+#define X(i, NB, NC, NT) &rem2d_class_ops_##i,
     REM2D_CLASSES(X)
 #undef X
 };
-
-// Build the world of every creature of this class (static creature -> lane mapping, used by rem2d_step).
-template <int NB, int NC, int NT>
-__global__ void __launch_bounds__(32) reset_kernel(float* state, const int* __restrict__ lane_creature, DevPop p) {
-    using SimT = Sim<NB, NC, NT>;
-    const int lane = threadIdx.x, batch = blockIdx.x;
-    SimT sim;
-    sim.g = state + (size_t)batch * SimT::WORDS * 32 + lane;
-    sim.build_world(p, lane_creature[batch * 32 + lane]);
-}
-
-// Whole episodes with dynamic lane refill: every lane pulls the next creature of its class from a queue
-// (big creatures first), builds its world in the lane's column of the warp's state block, ticks it until the
-// episode ends, writes fitness / ticks and pulls the next one. Lanes of a warp are therefore always busy until
-// the queue drains, instead of idling until the longest-lived creature of a fixed batch dies; and the cold
-// state of the few hundred resident warps stays L2-resident.
-template <int NB, int NC, int NT>
-__global__ void __launch_bounds__(32) episode_kernel(float* slots, const int* __restrict__ order, int n_order, int* queue,
-                                                     DevPop p, const Terrain* __restrict__ ter, const Consts* __restrict__ k,
-                                                     int max_ticks, double* fitness, int* ticks, int* alive, int* status,
-                                                     unsigned long long* counters) {
-    using SimT = Sim<NB, NC, NT>;
-    extern __shared__ float hot[];
-    const int lane = threadIdx.x;
-    SimT sim;
-    sim.g = slots + (size_t)blockIdx.x * SimT::WORDS * 32 + lane;
-    sim.h = hot + lane;
-    sim.ter = ter; sim.k = k;
-#pragma unroll
-    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
-    int my = -1;
-    bool exhausted = false;
-    for (;;) {
-        if (my < 0 && !exhausted) {
-            int idx = atomicAdd(queue, 1);
-            if (idx < n_order) { my = order[idx]; sim.build_world(p, my); }
-            else exhausted = true;
-        }
-        if (!__any_sync(0xffffffffu, my >= 0)) break;
-        if (my >= 0) {
-            sim.tick();
-            const int t = sim.Si(S_TICKS);
-            if (!sim.Si(S_ALIVE) || t >= max_ticks) {
-                fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = sim.Si(S_STATUS);
-                my = -1;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
-        unsigned long long v = sim.cnt.c[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicAdd(&counters[i], v);
-    }
-}
-
-// One warp per batch of 32 creatures; each lane advances its creature by up to n_ticks ticks.
-template <int NB, int NC, int NT>
-__global__ void __launch_bounds__(32) step_kernel(float* state, int n_ticks, const Terrain* __restrict__ ter,
-                                                  const Consts* __restrict__ k, unsigned long long* counters) {
-    using SimT = Sim<NB, NC, NT>;
-    extern __shared__ float hot[];
-    const int lane = threadIdx.x, batch = blockIdx.x;
-    SimT sim;
-    sim.g = state + (size_t)batch * SimT::WORDS * 32 + lane;
-    sim.h = hot + lane;
-    sim.ter = ter; sim.k = k;
-#pragma unroll
-    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
-    sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
-    if (sim.nb > 0) {
-        for (int t = 0; t < n_ticks; ++t) {
-            if (!sim.Si(S_ALIVE)) break;
-            sim.tick();
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
-        unsigned long long v = sim.cnt.c[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicAdd(&counters[i], v);
-    }
-}
+#define g_classes(k) (*g_classes_p[k])
 
 // fitness / ticks / alive / status of every creature of a class -> creature-indexed outputs
 __global__ void gather_kernel(const float* state, const int* __restrict__ lane_creature, int n_lanes, int words,
@@ -272,13 +174,8 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
     cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device);
-#define X(i, NB, NC, NT)                                                                                              \
-    if ((e = cudaFuncSetAttribute(step_kernel<NB, NC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                  Sim<NB, NC, NT>::HOT_WORDS * 128)) != cudaSuccess) return fail("cudaFuncSetAttribute", e); \
-    if ((e = cudaFuncSetAttribute(episode_kernel<NB, NC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                  Sim<NB, NC, NT>::HOT_WORDS * 128)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
-    REM2D_CLASSES(X)
-#undef X
+    for (int q = 0; q < N_CLASSES; ++q)
+        if ((e = g_classes(q).set_attributes()) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
     *out = h;
     return REM2D_OK;
 }
@@ -384,8 +281,8 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         int nb = pop->body_off[c + 1] - pop->body_off[c];
         if (nb < 1) { h->err = "upload: creature without a root body"; return REM2D_E_INVALID; }
         int k = -1;
-        for (int q = 0; q < N_CLASSES; ++q) if (nb <= g_classes[q].nb) { k = q; break; }
-        if (k < 0) { char buf[128]; snprintf(buf, sizeof(buf), "upload: creature %d has %d bodies (> %d supported)", c, nb, g_classes[N_CLASSES - 1].nb); h->err = buf; return REM2D_E_CAPACITY; }
+        for (int q = 0; q < N_CLASSES; ++q) if (nb <= g_classes(q).nb) { k = q; break; }
+        if (k < 0) { char buf[128]; snprintf(buf, sizeof(buf), "upload: creature %d has %d bodies (> %d supported)", c, nb, g_classes(N_CLASSES - 1).nb); h->err = buf; return REM2D_E_CAPACITY; }
         int j0 = pop->body_off[c] - c;
         for (int j = 0; j < nb - 1; ++j)
             if (pop->joint_parent[j0 + j] < 0 || pop->joint_parent[j0 + j] > j) { h->err = "upload: joint parent must precede its child"; return REM2D_E_INVALID; }
@@ -426,7 +323,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         cs.n_batches = (int)((m.size() + 31) / 32);
         cs.n_members = (int)m.size();
         {   // resident warps of the episode kernel: as many as fit next to each other on the SMs (227 KB shared memory each)
-            int per_sm = std::max(1, std::min(32, (227 * 1024) / (g_classes[k].hot_words * 128 + 1024)));
+            int per_sm = std::max(1, std::min(32, (227 * 1024) / (g_classes(k).hot_words * 128 + 1024)));
             cs.episode_grid = std::min(cs.n_batches, h->n_sms * per_sm);
         }
         CK(cudaMalloc(&cs.d_queue, sizeof(int)));
@@ -434,7 +331,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         for (size_t i = 0; i < m.size(); ++i) { cs.lane_creature[i] = m[i]; h->creature_lane[m[i]] = (int)i; }
         CK(cudaMalloc(&cs.d_lane_creature, cs.lane_creature.size() * sizeof(int)));
         CK(cudaMemcpy(cs.d_lane_creature, cs.lane_creature.data(), cs.lane_creature.size() * sizeof(int), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&cs.d_state, (size_t)cs.n_batches * g_classes[k].words * 32 * sizeof(float)));
+        CK(cudaMalloc(&cs.d_state, (size_t)cs.n_batches * g_classes(k).words * 32 * sizeof(float)));
     }
     CK(cudaMalloc(&h->d_fitness, sizeof(double) * std::max(n, 1)));
     CK(cudaMalloc(&h->d_ticks, sizeof(int) * std::max(n, 1)));
@@ -465,11 +362,7 @@ static int launch_reset(rem2d_handle* h) {
     for (int k = N_CLASSES - 1; k >= 0; --k) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
-        switch (k) {
-#define X(i, NB, NC, NT) case i: reset_kernel<NB, NC, NT><<<cs.n_batches, 32, 0, cs.stream>>>(cs.d_state, cs.d_lane_creature, h->dpop); break;
-            REM2D_CLASSES(X)
-#undef X
-        }
+        g_classes(k).reset(cs.n_batches, cs.stream, cs.d_state, cs.d_lane_creature, h->dpop);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -491,21 +384,55 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
         CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
-        switch (k) {
-#define X(i, NB, NC, NT)                                                                                             \
-    case i:                                                                                                          \
-        episode_kernel<NB, NC, NT><<<cs.episode_grid, 32, Sim<NB, NC, NT>::HOT_WORDS * 128, cs.stream>>>(           \
-            cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter, h->d_consts, max_ticks,     \
-            h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);                                       \
-        break;
-            REM2D_CLASSES(X)
-#undef X
-        }
+        g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
+                             h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
         h->launches++;
     }
     CK(cudaGetLastError());
     rc = join_streams(h);
     if (rc) return rc;
+    // Promotion: creatures that exceeded a capacity of their class (contact pool, TOI island) are re-run from tick 0
+    // in the next larger class until they fit. Rare (violent tick-1 limit snaps, flat-terrain pile-ups).
+    const int n = h->n_creatures;
+    std::vector<int> cls_of(h->creature_class);
+    for (int round = 0; round < N_CLASSES; ++round) {
+        CK(cudaMemcpyAsync(h->h_status.data(), h->d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, h->user_stream));
+        CK(cudaStreamSynchronize(h->user_stream));
+        std::vector<std::vector<int>> redo(N_CLASSES);
+        bool any = false;
+        for (int c = 0; c < n; ++c)
+            if (h->h_status[c]) {
+                if (cls_of[c] + 1 >= N_CLASSES) {
+                    char buf[160];
+                    snprintf(buf, sizeof(buf), "creature %d exceeds the capacities of the largest class (status %d)", c, h->h_status[c]);
+                    h->err = buf;
+                    return REM2D_E_CAPACITY;
+                }
+                cls_of[c] += 1;
+                redo[cls_of[c]].push_back(c);
+                any = true;
+            }
+        if (!any) break;
+        for (int k = 0; k < N_CLASSES; ++k) {
+            if (redo[k].empty()) continue;
+            ClassState& cs = h->cls[k];
+            int batches = (int)((redo[k].size() + 31) / 32);
+            int *d_order = nullptr, *d_queue = nullptr;
+            float* d_slots = nullptr;
+            CK(cudaMalloc(&d_order, sizeof(int) * redo[k].size()));
+            CK(cudaMalloc(&d_queue, sizeof(int)));
+            CK(cudaMalloc(&d_slots, (size_t)batches * g_classes(k).words * 32 * sizeof(float)));
+            CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
+            CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
+            g_classes(k).episode(batches, h->user_stream, d_slots, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter, h->d_consts,
+                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+            h->launches++;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(h->user_stream));
+            cudaFree(d_order); cudaFree(d_queue); cudaFree(d_slots);
+            (void)cs;
+        }
+    }
     CK(cudaEventRecord(h->ev_stop, h->user_stream));
     h->state_valid = false; h->results_valid = true;
     return REM2D_OK;
@@ -524,7 +451,7 @@ static int gather(rem2d_handle* h) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
         int n_lanes = cs.n_batches * 32;
-        gather_kernel<<<(n_lanes + 127) / 128, 128, 0, h->user_stream>>>(cs.d_state, cs.d_lane_creature, n_lanes, g_classes[k].words,
+        gather_kernel<<<(n_lanes + 127) / 128, 128, 0, h->user_stream>>>(cs.d_state, cs.d_lane_creature, n_lanes, g_classes(k).words,
                                                                         h->d_fitness, h->d_ticks, h->d_alive, h->d_status);
         h->launches++;
     }
@@ -558,15 +485,7 @@ int rem2d_step(rem2d_handle* h, int32_t n_ticks) {
     for (int k = N_CLASSES - 1; k >= 0; --k) {        // most expensive class first
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
-        switch (k) {
-#define X(i, NB, NC, NT)                                                                                             \
-    case i:                                                                                                          \
-        step_kernel<NB, NC, NT><<<cs.n_batches, 32, Sim<NB, NC, NT>::HOT_WORDS * 128, cs.stream>>>(                 \
-            cs.d_state, n_ticks, h->d_ter, h->d_consts, h->d_counters);                                              \
-        break;
-            REM2D_CLASSES(X)
-#undef X
-        }
+        g_classes(k).step(cs.n_batches, cs.stream, cs.d_state, n_ticks, h->d_ter, h->d_consts, h->d_counters);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -667,7 +586,7 @@ int rem2d_read_state(rem2d_handle* h, rem2d_state_view* out) {
     for (int k = 0; k < N_CLASSES; ++k) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
-        const ClassInfo& ci = g_classes[k];
+        const ClassOps& ci = g_classes(k);
         std::vector<float> st((size_t)cs.n_batches * ci.words * 32);
         CK(cudaMemcpy(st.data(), cs.d_state, st.size() * sizeof(float), cudaMemcpyDeviceToHost));
         auto asint = [](float f) { int i; memcpy(&i, &f, 4); return i; };

@@ -145,9 +145,9 @@ enum { CF_KEY, CF_TOI, CF_LNX, CF_LNY, CF_LPX, CF_LPY, CF_P0X, CF_P0Y, CF_P0N, C
 #define ST_POOL_OVERFLOW 1     // contact pool (NC) exhausted
 #define ST_TOI_OVERFLOW 4      // TOI mini-island larger than RB_TOI_ISLAND_CAP
 
-// hot (shared memory) layout, words per lane: 5*NB + 19*NJ + 21*NT
+// hot (shared memory) layout, words per lane: 5*NB + 17*NJ + 21*NT
 enum { HB_VX, HB_VY, HB_W, HB_INVM, HB_INVI, HB_COUNT };                 // position phase: CX, CY, A reuse 0..2
-enum { HJ_META, HJ_RAX, HJ_RAY, HJ_RBX, HJ_RBY, HJ_EXX, HJ_EYX, HJ_EZX, HJ_EYY, HJ_EZY, HJ_INV2, HJ_INV3, HJ_MMASS,
+enum { HJ_META, HJ_RAX, HJ_RAY, HJ_RBX, HJ_RBY, HJ_EXX, HJ_EYX, HJ_EYY, HJ_INV2, HJ_INV3, HJ_MMASS,
        HJ_IMPX, HJ_IMPY, HJ_IMPZ, HJ_MIMP, HJ_MSPEED, HJ_MAXIMP, HJ_COUNT };   // INV2/INV3: 1/det of the 2x2 / 3x3 blocks
 // position-phase overlay of a joint slot
 enum { PJ_META = HJ_META, PJ_LAAX, PJ_LAAY, PJ_LABX, PJ_LABY, PJ_LOWER, PJ_UPPER };
@@ -832,7 +832,8 @@ struct Sim {
         float exx = HJ(HJ_EXX, s), eyx = HJ(HJ_EYX, s), eyy = HJ(HJ_EYY, s);
         const float d2 = HJ(HJ_INV2, s);
         if (limit != 0) {
-            float ezx = HJ(HJ_EZX, s), ezy = HJ(HJ_EZY, s), ezz = iA + iB;
+            // third row/column of the effective mass, same expressions as b2RevoluteJoint::InitVelocityConstraints
+            float ezx = -rA.y * iA - rB.y * iB, ezy = rA.x * iA + rB.x * iB, ezz = iA + iB;
             V2 Cdot1 = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
             float Cdot2 = wB - wA;
             // Solve33: ex = (exx, eyx, ezx), ey = (eyx, eyy, ezy), ez = (ezx, ezy, ezz)
@@ -1005,7 +1006,7 @@ struct Sim {
             HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
             HJ(HJ_META, s) = __int_as_float(a | (b << 8) | (limit << 16) | (j << 24));
             HJ(HJ_RAX, s) = rA.x; HJ(HJ_RAY, s) = rA.y; HJ(HJ_RBX, s) = rB.x; HJ(HJ_RBY, s) = rB.y;
-            HJ(HJ_EXX, s) = exx; HJ(HJ_EYX, s) = eyx; HJ(HJ_EZX, s) = ezx; HJ(HJ_EYY, s) = eyy; HJ(HJ_EZY, s) = ezy;
+            HJ(HJ_EXX, s) = exx; HJ(HJ_EYX, s) = eyx; HJ(HJ_EYY, s) = eyy;
             {
                 float inv2 = exx * eyy - eyx * eyx;
                 if (inv2 != 0.0f) inv2 = 1.0f / inv2;

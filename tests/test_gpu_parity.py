@@ -107,3 +107,19 @@ def test_episode_kernel_matches_stepping_kernel():
         g.step(1)                      # stepping state was consumed by the episode kernel
     g.reset(); g.step(3)
     assert (g.read_state()["ticks"] == 3).all()
+
+
+def test_capacity_overflow_is_promoted_to_a_larger_class():
+    """A terrain with very short edges makes every body overlap dozens of edge proxies: the contact pool of the
+    creature's own class overflows and the library must transparently re-run it in a larger class."""
+    random.seed(41)
+    pop = flatten_population([Individual.random(encoding="direct") for _ in range(96)])
+    ys = np.full(200, 5.0)
+    step = 0.06                       # 199 edges cover x in [0, 11.9]; a 1 m wide box spans ~20 of them
+    g, o = Engine(device=0), OracleEngine(threads=8)
+    for e in (g, o):
+        e.set_terrain(ys, step)
+    fg, tg = g.evaluate(pop, 150)
+    fo, to = o.evaluate(pop, 150)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo)
+    assert g.counters() == o.counters()
