@@ -38,6 +38,48 @@ __global__ void gather_kernel(const float* state, const int* __restrict__ lane_c
     status[c] = __float_as_int(g[S_STATUS * 32]);
 }
 
+// ---- survivor compaction between tick phases of the evaluate path -------------------------------------------------
+// plan: every lane whose episode ended (dead, tick budget reached, or a capacity overflow) writes its result; every
+// survivor gets a dense destination slot (order within the class is irrelevant for results).
+__global__ void compact_plan_kernel(const float* state, const int* __restrict__ lane_creature, int n_lanes, int words, int max_ticks,
+                                    double* fitness, int* ticks, int* alive, int* status, int* dst_slot, int* n_alive) {
+    int gl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= n_lanes) return;
+    int c = lane_creature[gl];
+    int dst = -1;
+    if (c >= 0) {
+        const float* g = state + (size_t)(gl >> 5) * words * 32 + (gl & 31);
+        int a = __float_as_int(g[S_ALIVE * 32]), t = __float_as_int(g[S_TICKS * 32]), st = __float_as_int(g[S_STATUS * 32]);
+        if (!a || st || t >= max_ticks) {
+            fitness[c] = __hiloint2double(__float_as_int(g[S_FIT_HI * 32]), __float_as_int(g[S_FIT_LO * 32]));
+            ticks[c] = t; alive[c] = a; status[c] = st;
+        } else dst = atomicAdd(n_alive, 1);
+    }
+    dst_slot[gl] = dst;
+}
+// copy: one CTA per source lane moves the creature's column into its slot of the other (ping-pong) buffer
+__global__ void compact_copy_kernel(const float* src, float* dst, const int* __restrict__ dst_slot, const int* __restrict__ src_creature,
+                                    int* dst_creature, int words) {
+    int gl = blockIdx.x;
+    int d = dst_slot[gl];
+    if (d < 0) return;
+    const float* s = src + (size_t)(gl >> 5) * words * 32 + (gl & 31);
+    float* o = dst + (size_t)(d >> 5) * words * 32 + (d & 31);
+    for (int w = threadIdx.x; w < words; w += blockDim.x) o[w * 32] = s[w * 32];
+    if (threadIdx.x == 0) dst_creature[d] = src_creature[gl];
+}
+// pad: the unused lanes of the last destination batch become empty lanes
+__global__ void compact_pad_kernel(float* dst, int* dst_creature, int words, const int* n_alive) {
+    int n = *n_alive;
+    if (n == 0 || (n & 31) == 0) return;
+    int d = n + threadIdx.x;
+    if ((d >> 5) != ((n - 1) >> 5)) return;
+    float* o = dst + (size_t)(d >> 5) * words * 32 + (d & 31);
+    o[S_NB * 32] = __int_as_float(0);
+    o[S_ALIVE * 32] = __int_as_float(0);
+    dst_creature[d] = -1;
+}
+
 // FP32 issue-rate microbenchmark: 8 independent multiply / add chains per thread. The step kernel is built with
 // -fmad=false (parity), so its ceiling is the non-fused FMUL/FADD issue rate: 1 FLOP per lane per cycle.
 __global__ void fp32_issue_kernel(float* out, int iters, float b, float c) {
@@ -58,6 +100,18 @@ struct ClassState {
     float* d_state = nullptr;
     int* d_lane_creature = nullptr;
     int* d_queue = nullptr;
+    // phased evaluation with survivor compaction (ping-pong buffers)
+    float* d_state2 = nullptr;
+    int* d_lc_work[2] = {nullptr, nullptr};   // lane -> creature maps of the compacted phases (d_lane_creature stays the static map)
+    const int* lc_cur = nullptr;
+    int lc_next = 0;
+    int done_ticks = 0;
+    int* d_dst_slot = nullptr;
+    int* d_n_alive = nullptr;
+    int* h_n_alive = nullptr;            // pinned
+    int cur_lanes = 0;                  // lanes (padded to 32) of the current phase
+    int phase = 0;
+    bool active = false, pending = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
 };
@@ -105,6 +159,13 @@ static void free_population(rem2d_handle* h) {
         if (c.d_state) cudaFree(c.d_state);
         if (c.d_lane_creature) cudaFree(c.d_lane_creature);
         if (c.d_queue) cudaFree(c.d_queue);
+        if (c.d_state2) cudaFree(c.d_state2);
+        if (c.d_lc_work[0]) cudaFree(c.d_lc_work[0]);
+        if (c.d_lc_work[1]) cudaFree(c.d_lc_work[1]);
+        if (c.d_dst_slot) cudaFree(c.d_dst_slot);
+        if (c.d_n_alive) cudaFree(c.d_n_alive);
+        if (c.h_n_alive) cudaFreeHost(c.h_n_alive);
+        c.d_state2 = nullptr; c.d_lc_work[0] = c.d_lc_work[1] = nullptr; c.d_dst_slot = nullptr; c.d_n_alive = nullptr; c.h_n_alive = nullptr;
         c.d_state = nullptr; c.d_lane_creature = nullptr; c.d_queue = nullptr; c.n_batches = 0; c.n_members = 0; c.lane_creature.clear();
     }
     if (h->d_fitness) cudaFree(h->d_fitness);
@@ -332,6 +393,12 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         CK(cudaMalloc(&cs.d_lane_creature, cs.lane_creature.size() * sizeof(int)));
         CK(cudaMemcpy(cs.d_lane_creature, cs.lane_creature.data(), cs.lane_creature.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&cs.d_state, (size_t)cs.n_batches * g_classes(k).words * 32 * sizeof(float)));
+        CK(cudaMalloc(&cs.d_state2, (size_t)cs.n_batches * g_classes(k).words * 32 * sizeof(float)));
+        CK(cudaMalloc(&cs.d_lc_work[0], cs.lane_creature.size() * sizeof(int)));
+        CK(cudaMalloc(&cs.d_lc_work[1], cs.lane_creature.size() * sizeof(int)));
+        CK(cudaMalloc(&cs.d_dst_slot, cs.lane_creature.size() * sizeof(int)));
+        CK(cudaMalloc(&cs.d_n_alive, sizeof(int)));
+        CK(cudaMallocHost(&cs.h_n_alive, sizeof(int)));
     }
     CK(cudaMalloc(&h->d_fitness, sizeof(double) * std::max(n, 1)));
     CK(cudaMalloc(&h->d_ticks, sizeof(int) * std::max(n, 1)));
@@ -355,6 +422,11 @@ static int join_streams(rem2d_handle* h) {
     return REM2D_OK;
 }
 
+static int join_streams_all(rem2d_handle* h) {
+    for (auto& c : h->cls) if (c.n_batches) { CK(cudaEventRecord(c.done, c.stream)); CK(cudaStreamWaitEvent(h->user_stream, c.done, 0)); }
+    return REM2D_OK;
+}
+
 static int launch_reset(rem2d_handle* h) {
     if (!h->have_terrain) { h->err = "reset: no terrain set"; return REM2D_E_INVALID; }
     int rc = fork_streams(h);
@@ -373,26 +445,9 @@ static int launch_reset(rem2d_handle* h) {
     return REM2D_OK;
 }
 
-// Whole episodes for the uploaded population on the persistent episode kernels (one per class, concurrent).
-static int launch_episodes(rem2d_handle* h, int max_ticks) {
-    if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
-    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
-    CK(cudaEventRecord(h->ev_start, h->user_stream));
-    int rc = fork_streams(h);
-    if (rc) return rc;
-    for (int k = N_CLASSES - 1; k >= 0; --k) {
-        ClassState& cs = h->cls[k];
-        if (!cs.n_batches) continue;
-        CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
-        g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
-                             h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
-        h->launches++;
-    }
-    CK(cudaGetLastError());
-    rc = join_streams(h);
-    if (rc) return rc;
-    // Promotion: creatures that exceeded a capacity of their class (contact pool, TOI island) are re-run from tick 0
-    // in the next larger class until they fit. Rare (violent tick-1 limit snaps, flat-terrain pile-ups).
+// Promotion: creatures that exceeded a capacity of their class (contact pool) are re-run from tick 0 on the refill
+// episode kernel of the next larger class until they fit. Rare (very fine terrains, pile-ups).
+static int promote_overflowed(rem2d_handle* h, int max_ticks) {
     const int n = h->n_creatures;
     std::vector<int> cls_of(h->creature_class);
     for (int round = 0; round < N_CLASSES; ++round) {
@@ -433,6 +488,109 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
             (void)cs;
         }
     }
+    return REM2D_OK;
+}
+
+// Whole episodes in tick phases with survivor compaction (default evaluate path).
+// Every class advances independently on its own stream: step_kernel(phase ticks) -> plan (harvest finished creatures,
+// assign dense slots to survivors) -> copy columns into the other buffer -> the host reads the survivor count and
+// launches the next, smaller phase. Almost every creature of a random population dies when the wall of death reaches
+// the start pad (tick ~126), so the first phase is 128 ticks; afterwards the few survivors are repacked every 32 ticks
+// instead of keeping their original warps alive at 1-3 live lanes out of 32.
+static int launch_phased(rem2d_handle* h, int max_ticks) {
+    if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
+    CK(cudaEventRecord(h->ev_start, h->user_stream));
+    int rc = launch_reset(h);           // builds every world into the static batches (also zeroes the counters)
+    if (rc) return rc;
+    rc = fork_streams(h);
+    if (rc) return rc;
+    int n_active = 0;
+    for (int k = N_CLASSES - 1; k >= 0; --k) {
+        ClassState& cs = h->cls[k];
+        cs.active = cs.n_batches > 0; cs.pending = false; cs.phase = 0; cs.cur_lanes = cs.n_batches * 32;
+        cs.lc_cur = cs.d_lane_creature; cs.lc_next = 0; cs.done_ticks = 0;
+        if (cs.active) ++n_active;
+    }
+    const int first_phase = 128, next_phase = 32;
+    auto enqueue = [&](int k) -> int {
+        ClassState& cs = h->cls[k];
+        const int words = g_classes(k).words;
+        const int batches = cs.cur_lanes / 32;
+        int ticks = cs.phase == 0 ? first_phase : next_phase;
+        if (ticks > max_ticks - cs.done_ticks) ticks = max_ticks - cs.done_ticks;
+        cs.done_ticks += ticks;
+        int* lc_dst = cs.d_lc_work[cs.lc_next];
+        g_classes(k).step(batches, cs.stream, cs.d_state, ticks, h->d_ter, h->d_consts, h->d_counters);
+        CK(cudaMemsetAsync(cs.d_n_alive, 0, sizeof(int), cs.stream));
+        compact_plan_kernel<<<(cs.cur_lanes + 127) / 128, 128, 0, cs.stream>>>(cs.d_state, cs.lc_cur, cs.cur_lanes, words, max_ticks,
+                                                                              h->d_fitness, h->d_ticks, h->d_alive, h->d_status,
+                                                                              cs.d_dst_slot, cs.d_n_alive);
+        compact_copy_kernel<<<cs.cur_lanes, 128, 0, cs.stream>>>(cs.d_state, cs.d_state2, cs.d_dst_slot, cs.lc_cur, lc_dst, words);
+        compact_pad_kernel<<<1, 32, 0, cs.stream>>>(cs.d_state2, lc_dst, words, cs.d_n_alive);
+        CK(cudaMemcpyAsync(cs.h_n_alive, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, cs.stream));
+        CK(cudaGetLastError());
+        h->launches += 4;
+        cs.pending = true;
+        return REM2D_OK;
+    };
+    for (int k = N_CLASSES - 1; k >= 0; --k)
+        if (h->cls[k].active) { rc = enqueue(k); if (rc) return rc; }
+    while (n_active > 0) {
+        bool progressed = false;
+        for (int k = N_CLASSES - 1; k >= 0; --k) {
+            ClassState& cs = h->cls[k];
+            if (!cs.active || !cs.pending) continue;
+            cudaError_t q = cudaStreamQuery(cs.stream);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) { h->err = std::string("phase: ") + cudaGetErrorString(q); return REM2D_E_CUDA; }
+            progressed = true;
+            cs.pending = false;
+            std::swap(cs.d_state, cs.d_state2);
+            cs.lc_cur = cs.d_lc_work[cs.lc_next];
+            cs.lc_next ^= 1;
+            int alive = *cs.h_n_alive;
+            cs.phase++;
+            // creatures that reached the tick budget were harvested by the plan kernel, so alive == 0 ends the class
+            if (alive == 0) { cs.active = false; --n_active; continue; }
+            cs.cur_lanes = ((alive + 31) / 32) * 32;
+            rc = enqueue(k);
+            if (rc) return rc;
+        }
+        if (!progressed) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    rc = join_streams_all(h);
+    if (rc) return rc;
+    rc = promote_overflowed(h, max_ticks);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_stop, h->user_stream));
+    h->state_valid = false; h->results_valid = true;
+    return REM2D_OK;
+}
+
+// Whole episodes for the uploaded population on the persistent episode kernels (one per class, concurrent).
+static int launch_episodes(rem2d_handle* h, int max_ticks) {
+    if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
+    CK(cudaEventRecord(h->ev_start, h->user_stream));
+    int rc = fork_streams(h);
+    if (rc) return rc;
+    for (int k = N_CLASSES - 1; k >= 0; --k) {
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches) continue;
+        CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
+        g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
+                             h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    rc = join_streams(h);
+    if (rc) return rc;
+    rc = promote_overflowed(h, max_ticks);
+    if (rc) return rc;
     CK(cudaEventRecord(h->ev_stop, h->user_stream));
     h->state_valid = false; h->results_valid = true;
     return REM2D_OK;
@@ -519,7 +677,10 @@ int rem2d_run_episodes(rem2d_handle* h, int32_t max_ticks) {
     if (!h) return REM2D_E_INVALID;
     if (!h->have_pop || max_ticks < 0) { h->err = "run_episodes: no population / negative tick count"; return REM2D_E_INVALID; }
     cudaSetDevice(h->cfg.device);
-    int rc = launch_episodes(h, max_ticks);
+    // REM2D_EPISODE_MODE=refill selects the persistent per-lane-refill kernel (better when the population is many times
+    // larger than the resident lanes); the default runs tick phases with survivor compaction.
+    const char* mode = getenv("REM2D_EPISODE_MODE");
+    int rc = (mode && !strcmp(mode, "refill")) ? launch_episodes(h, max_ticks) : launch_phased(h, max_ticks);
     if (rc) return rc;
     CK(cudaEventSynchronize(h->ev_stop));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev_start, h->ev_stop));

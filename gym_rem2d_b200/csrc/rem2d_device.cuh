@@ -50,7 +50,7 @@ namespace rem2d {
 #define RB_MAX_POLY_VERTS 16   // pybox2d build value; bounds the TOI push-back loop only
 
 #define RB_MAX_EDGES 200       // terrain edges (199 used)
-#define RB_TOI_ISLAND_CAP 12   // touching contacts of ONE module in a TOI mini-island
+#define RB_TOI_ISLAND_CAP 32   // b2_maxTOIContacts: Box2D stops adding contacts to a TOI mini-island at 32
 
 struct V2 { float x, y; };
 struct Rot { float s, c; };
@@ -143,7 +143,6 @@ enum { CF_KEY, CF_TOI, CF_LNX, CF_LNY, CF_LPX, CF_LPY, CF_P0X, CF_P0Y, CF_P0N, C
 #define MT_FACE_B 2
 // status bits
 #define ST_POOL_OVERFLOW 1     // contact pool (NC) exhausted
-#define ST_TOI_OVERFLOW 4      // TOI mini-island larger than RB_TOI_ISLAND_CAP
 
 // hot (shared memory) layout, words per lane: 5*NB + 17*NJ + 21*NT
 enum { HB_VX, HB_VY, HB_W, HB_INVM, HB_INVI, HB_COUNT };                 // position phase: CX, CY, A reuse 0..2
@@ -1418,7 +1417,7 @@ struct Sim {
                 int key = Ci(CF_KEY, c);
                 if (key_body(key) != mb) continue;
                 if (key_flags(key) & CK_ISLAND) continue;
-                if (ni == RB_TOI_ISLAND_CAP) { setSi(S_STATUS, Si(S_STATUS) | ST_TOI_OVERFLOW); break; }
+                if (ni == RB_TOI_ISLAND_CAP) break;
                 int e = key_edge(key);
                 bool inIsland = false;
                 for (int i = 0; i < ni; ++i) inIsland |= (key_edge(Ci(CF_KEY, isl[i])) == e);

@@ -115,7 +115,7 @@ def test_capacity_overflow_is_promoted_to_a_larger_class():
     random.seed(41)
     pop = flatten_population([Individual.random(encoding="direct") for _ in range(96)])
     ys = np.full(200, 5.0)
-    step = 0.06                       # 199 edges cover x in [0, 11.9]; a 1 m wide box spans ~20 of them
+    step = 0.15                       # 199 edges cover x in [0, 29.9]; a 1 m wide box overlaps ~12 edge proxies
     g, o = Engine(device=0), OracleEngine(threads=8)
     for e in (g, o):
         e.set_terrain(ys, step)
