@@ -677,10 +677,11 @@ int rem2d_run_episodes(rem2d_handle* h, int32_t max_ticks) {
     if (!h) return REM2D_E_INVALID;
     if (!h->have_pop || max_ticks < 0) { h->err = "run_episodes: no population / negative tick count"; return REM2D_E_INVALID; }
     cudaSetDevice(h->cfg.device);
-    // REM2D_EPISODE_MODE=refill selects the persistent per-lane-refill kernel (better when the population is many times
-    // larger than the resident lanes); the default runs tick phases with survivor compaction.
+    // Default: persistent kernel with per-lane refill. REM2D_EPISODE_MODE=phased selects tick phases with survivor
+    // compaction instead (measured slower at pop 65536: the run is bound by the sequential ticks of the longest-lived
+    // large creature, and phases add a launch/sync per 32 ticks to exactly that critical path).
     const char* mode = getenv("REM2D_EPISODE_MODE");
-    int rc = (mode && !strcmp(mode, "refill")) ? launch_episodes(h, max_ticks) : launch_phased(h, max_ticks);
+    int rc = (mode && !strcmp(mode, "phased")) ? launch_phased(h, max_ticks) : launch_episodes(h, max_ticks);
     if (rc) return rc;
     CK(cudaEventSynchronize(h->ev_stop));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev_start, h->ev_stop));

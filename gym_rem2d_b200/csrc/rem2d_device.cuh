@@ -108,10 +108,26 @@ __device__ __forceinline__ void sincos_kernel(double x, double& s, double& c) {
     else if (n == 2) { s = -sr; c = -cr; }
     else { s = -cr; c = sr; }
 }
+// b2Rot::Set: float kernel, same operation sequence as oracle sincos_kernel_f32 (Cody-Waite by pi/2 with short
+// constants + Cephes-style minimax polynomials); huge angles use the double kernel.
 __device__ __forceinline__ Rot rot_set(float a) {
-    double s, c;
-    sincos_kernel((double)a, s, c);
-    Rot q; q.s = (float)s; q.c = (float)c;
+    Rot q;
+    if (!(abs2(a) < 65536.0f)) {
+        double s, c;
+        sincos_kernel((double)a, s, c);
+        q.s = (float)s; q.c = (float)c;
+        return q;
+    }
+    float kf = floorf(a * 0.636619747f + 0.5f);
+    float r = ((a - kf * 1.5703125f) - kf * 4.837512969970703125e-4f) - kf * 7.54978995489188216e-8f;
+    float z = r * r;
+    float sr = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    float cr = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+    int n = (int)kf & 3;
+    if (n == 0) { q.s = sr; q.c = cr; }
+    else if (n == 1) { q.s = cr; q.c = -sr; }
+    else if (n == 2) { q.s = -sr; q.c = -cr; }
+    else { q.s = -cr; q.c = sr; }
     return q;
 }
 
@@ -423,8 +439,13 @@ struct Sim {
         int nc = Si(S_NC);
         int key = Ci(CF_KEY, i);
         if ((key_flags(key) >> CK_COUNT_SHIFT) & 3) set_awake(key_body(key), true);
-        for (int k = i; k < nc - 1; ++k)
-            for (int f = 0; f < CF_COUNT; ++f) C(f, k) = C(f, k + 1);
+        for (int k = i; k < nc - 1; ++k) {
+            float tmp[CF_COUNT];                      // all loads first: 16 independent global loads in flight
+#pragma unroll
+            for (int f = 0; f < CF_COUNT; ++f) tmp[f] = C(f, k + 1);
+#pragma unroll
+            for (int f = 0; f < CF_COUNT; ++f) C(f, k) = tmp[f];
+        }
         setSi(S_NC, nc - 1);
     }
 

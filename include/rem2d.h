@@ -57,8 +57,8 @@ typedef struct rem2d_config {
                                   (Modular2DEnv.py:642-649, REM2D_main.py:370-377); 0: fixed horizon */
     int32_t device;            /* CUDA device ordinal (ignored by the oracle) */
     void* stream;              /* cudaStream_t to order work on; NULL = default stream */
-    int32_t sincos_mode;       /* oracle only: 0 = portable sin/cos (bit-identical to the CUDA build),
-                                  1 = libm sinf/cosf as upstream Box2D's b2Rot::Set */
+    int32_t sincos_mode;       /* oracle only: 0 = portable float sin/cos (bit-identical to the CUDA build),
+                                  1 = libm sinf/cosf as upstream Box2D's b2Rot::Set, 2 = portable double kernel */
     int32_t reserved;
 } rem2d_config;
 

@@ -223,10 +223,9 @@ static inline Xf xfmulT(Xf A, Xf B) {
 }
 
 /* ---------------------------------------------------------------- sin / cos
- * b2Rot::Set uses libm sinf/cosf. Mode 0 ("portable") evaluates sin/cos through double precision with
- * a fixed operation order so the CUDA build can reproduce it bit for bit: 3-term Cody-Waite reduction
- * by pi/2 and the classic degree-13/14 minimax kernels; the float result is the rounding of a value
- * accurate to ~1e-16, i.e. correctly rounded except in ~1e-8 of cases (libm sinf is within 1 ulp too). */
+ * b2Rot::Set uses libm sinf/cosf (mode 1). Mode 0 ("portable", default) is a float kernel with a fixed
+ * operation order that the CUDA build reproduces bit for bit; mode 2 is the same idea in double precision
+ * (3-term Cody-Waite by pi/2 + degree-13/14 minimax; also used for the controllers' double-precision sin). */
 static const double PIO2_1 = 1.57079632673412561417e+00;  /* first 33 bits of pi/2 */
 static const double PIO2_2 = 6.07710050630396597660e-11;  /* next 33 bits */
 static const double PIO2_2T = 2.02226624879595063154e-21; /* tail */
@@ -250,11 +249,35 @@ static inline void sincos_kernel(double x, double* s, double* c) {
     default: *s = -cr; *c = sr; break;
     }
 }
+/* Float variant used for body rotations (mode 0): Cody-Waite by pi/2 with short constants + Cephes-style minimax
+ * kernels, plain float mul/add in a fixed order. Over 100 ticks it tracks the libm build as closely as the double
+ * kernel does (tests/test_oracle.py); huge angles fall back to the double kernel. */
+static inline void sincos_kernel_f32(float a, float* s, float* c) {
+    if (!(fabs2(a) < 65536.0f)) {
+        double ds, dc;
+        sincos_kernel((double)a, &ds, &dc);
+        *s = (float)ds; *c = (float)dc;
+        return;
+    }
+    float kf = floorf(a * 0.636619747f + 0.5f);
+    float r = ((a - kf * 1.5703125f) - kf * 4.837512969970703125e-4f) - kf * 7.54978995489188216e-8f;
+    float z = r * r;
+    float sr = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    float cr = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+    int n = (int)kf & 3;
+    switch (n) {
+    case 0: *s = sr; *c = cr; break;
+    case 1: *s = cr; *c = -sr; break;
+    case 2: *s = -sr; *c = -cr; break;
+    default: *s = -cr; *c = sr; break;
+    }
+}
 static int g_sincos_mode = 0; /* set per step call from cfg (all handles of a process share it) */
 static inline Rot rot_set(float a) {
     Rot q;
     if (g_sincos_mode == 1) { q.s = sinf(a); q.c = cosf(a); return q; }
-    double s, c;
+    if (g_sincos_mode == 0) { sincos_kernel_f32(a, &q.s, &q.c); return q; }
+    double s, c;                 /* mode 2: double-precision portable kernel */
     sincos_kernel((double)a, &s, &c);
     q.s = (float)s; q.c = (float)c;
     return q;

@@ -151,21 +151,39 @@ def test_wall_of_death_lifetime_and_fitness_latch():
 
 
 def test_sincos_modes_agree_over_100_ticks():
-    """portable sin/cos (bit-identical to the CUDA build) vs libm sinf/cosf as upstream Box2D uses."""
+    """portable sin/cos (mode 0 float = what the CUDA build uses, mode 2 double) vs libm sinf/cosf (mode 1) as
+    upstream Box2D uses: both portable kernels must track the libm build equally well."""
     random.seed(11)
     pop = flatten_population([Individual.random(encoding="direct") for _ in range(16)])
     xs, ys = terrain.generate_terrain()
     out = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         e = OracleEngine(sincos_mode=mode)
         e.set_terrain(ys, K.TERRAIN_STEP)
         e.upload(pop)
         e.step(100)
         out.append(e.read_state()["pose"])
-    err = np.abs(out[0] - out[1]) / np.maximum(1.0, np.abs(out[1]))
-    # chaotic divergence after contact events is expected for a few creatures; the bulk must agree tightly
-    assert np.median(err) < 1e-5
-    assert np.mean(err.max(axis=1) < 1e-4) > 0.7
+    for k in (0, 2):
+        err = np.abs(out[k] - out[1]) / np.maximum(1.0, np.abs(out[1]))
+        # chaotic divergence after contact events is expected for a few creatures; the bulk must agree tightly
+        assert np.median(err) < 1e-5
+        assert np.mean(err.max(axis=1) < 1e-4) > 0.7
+
+
+def test_portable_float_sincos_is_accurate():
+    """rot_set mode 0 against float64 math over a wide angle range (via a free-spinning body's cached rotation is
+    not exposed, so the kernel is restated here in numpy float32 with the same operation order)."""
+    a = np.concatenate([np.linspace(-40, 40, 200001), np.linspace(-7000, 7000, 100001)]).astype(F32)
+    kf = np.floor(a * F32(0.636619747) + F32(0.5)).astype(F32)
+    r = ((a - kf * F32(1.5703125)) - kf * F32(4.837512969970703125e-4)) - kf * F32(7.54978995489188216e-8)
+    z = r * r
+    sr = ((F32(-1.9515295891e-4) * z + F32(8.3321608736e-3)) * z - F32(1.6666654611e-1)) * z * r + r
+    cr = ((F32(2.443315711809948e-5) * z - F32(1.388731625493765e-3)) * z + F32(4.166664568298827e-2)) * z * z - F32(0.5) * z + F32(1.0)
+    n = kf.astype(np.int64) & 3
+    s = np.where(n == 0, sr, np.where(n == 1, cr, np.where(n == 2, -sr, -cr)))
+    c = np.where(n == 0, cr, np.where(n == 1, -sr, np.where(n == 2, -cr, sr)))
+    assert np.abs(s - np.sin(a.astype(np.float64))).max() < 2.5e-7
+    assert np.abs(c - np.cos(a.astype(np.float64))).max() < 2.5e-7
 
 
 def test_counters_and_threads_are_consistent():
