@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB = os.path.join(HERE, "csrc", "librem2d_cuda.so")
+CUDA_LIB = os.environ.get("REM2D_CUDA_LIB") or os.path.join(HERE, "csrc", "librem2d_cuda.so")   # env override: A/B builds
 
 N_COUNTERS = 12
 COUNTER_NAMES = ["ticks", "body_ticks", "joint_vsolves", "p1_vsolves", "m2_vsolves", "joint_psolves",

@@ -383,10 +383,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         ClassState& cs = h->cls[k];
         cs.n_batches = (int)((m.size() + 31) / 32);
         cs.n_members = (int)m.size();
-        {   // resident warps of the episode kernel: as many as fit next to each other on the SMs (227 KB shared memory each)
-            int per_sm = std::max(1, std::min(32, (227 * 1024) / (g_classes(k).hot_words * 128 + 1024)));
-            cs.episode_grid = std::min(cs.n_batches, h->n_sms * per_sm);
-        }
+        cs.episode_grid = cs.n_batches;     // sized below once every class is known
         CK(cudaMalloc(&cs.d_queue, sizeof(int)));
         cs.lane_creature.assign((size_t)cs.n_batches * 32, -1);
         for (size_t i = 0; i < m.size(); ++i) { cs.lane_creature[i] = m[i]; h->creature_lane[m[i]] = (int)i; }
@@ -399,6 +396,41 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         CK(cudaMalloc(&cs.d_dst_slot, cs.lane_creature.size() * sizeof(int)));
         CK(cudaMalloc(&cs.d_n_alive, sizeof(int)));
         CK(cudaMallocHost(&cs.h_n_alive, sizeof(int)));
+    }
+    {   // Resident warps of the persistent episode kernels. All classes run concurrently, so the shared memory of the SMs
+        // (227 KB each) is divided among them in proportion to their work (bodies to simulate); a class never gets more
+        // warps than it has batches, and what it cannot use is handed to the others. Without this the largest class
+        // would occupy every SM until its last creature dies and the remaining classes would run after it.
+        double budget = (double)h->n_sms * 227.0 * 1024.0 * 0.98;
+        double work[N_CLASSES], smem[N_CLASSES];
+        bool fixed[N_CLASSES];
+        for (int k = 0; k < N_CLASSES; ++k) {
+            work[k] = 0.0; fixed[k] = members[k].empty(); smem[k] = g_classes(k).hot_words * 128.0 + 1024.0;
+            for (int c : members[k]) work[k] += 1.0 + (pop->body_off[c + 1] - pop->body_off[c]);
+            h->cls[k].episode_grid = 0;
+        }
+        for (int round = 0; round < N_CLASSES; ++round) {
+            double wsum = 0.0;
+            for (int k = 0; k < N_CLASSES; ++k) if (!fixed[k]) wsum += work[k];
+            if (wsum <= 0.0) break;
+            bool changed = false;
+            for (int k = 0; k < N_CLASSES; ++k) {
+                if (fixed[k]) continue;
+                int want = (int)(budget * work[k] / wsum / smem[k]);
+                if (want >= h->cls[k].n_batches) {        // the class fits entirely: fix it and give the rest back
+                    h->cls[k].episode_grid = h->cls[k].n_batches;
+                    budget -= h->cls[k].n_batches * smem[k];
+                    fixed[k] = true; changed = true;
+                }
+            }
+            if (!changed) {
+                for (int k = 0; k < N_CLASSES; ++k)
+                    if (!fixed[k]) h->cls[k].episode_grid = std::max(1, (int)(budget * work[k] / wsum / smem[k]));
+                break;
+            }
+        }
+        for (int k = 0; k < N_CLASSES; ++k)
+            if (h->cls[k].n_batches && h->cls[k].episode_grid < 1) h->cls[k].episode_grid = 1;
     }
     CK(cudaMalloc(&h->d_fitness, sizeof(double) * std::max(n, 1)));
     CK(cudaMalloc(&h->d_ticks, sizeof(int) * std::max(n, 1)));

@@ -830,13 +830,21 @@ struct Sim {
     }
 
     // ---- revolute joints in shared memory (b2RevoluteJoint)
+    // One b2RevoluteJoint::SolveVelocityConstraints. Lanes of a warp disagree on the limit state of their s-th joint,
+    // so a branchy version executes the 2x2 (limit inactive) and the 3x3 (at a limit) paths one after the other.
+    // Here both candidates are computed unconditionally from the same inputs and the results are selected: the two
+    // dependency chains overlap, there is no reconvergence overhead, and every value is bit-identical to the branchy
+    // evaluation (each candidate uses exactly the operations of its Box2D path).
     __device__ __forceinline__ void joint_solve_velocity(int s) {
-        int meta = HJi(HJ_META, s);
-        int a = meta & 0xff, b = (meta >> 8) & 0xff, limit = (meta >> 16) & 3;
-        float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+        const int meta = HJi(HJ_META, s);
+        const int a = meta & 0xff, b = (meta >> 8) & 0xff, limit = (meta >> 16) & 3;
+        const float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
         V2 vA = mk(HB(HB_VX, a), HB(HB_VY, a)); float wA = HB(HB_W, a);
         V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
-        V2 rA = mk(HJ(HJ_RAX, s), HJ(HJ_RAY, s)), rB = mk(HJ(HJ_RBX, s), HJ(HJ_RBY, s));
+        const V2 rA = mk(HJ(HJ_RAX, s), HJ(HJ_RAY, s)), rB = mk(HJ(HJ_RBX, s), HJ(HJ_RBY, s));
+        const float exx = HJ(HJ_EXX, s), eyx = HJ(HJ_EYX, s), eyy = HJ(HJ_EYY, s);
+        const float d2 = HJ(HJ_INV2, s), det = HJ(HJ_INV3, s);
+        const float jx = HJ(HJ_IMPX, s), jy = HJ(HJ_IMPY, s), jz = HJ(HJ_IMPZ, s);
         {   // motor
             float Cdot = wB - wA - HJ(HJ_MSPEED, s);
             float impulse = -HJ(HJ_MMASS, s) * Cdot;
@@ -847,50 +855,39 @@ struct Sim {
             impulse = ni - oldImpulse;
             wA -= iA * impulse; wB += iB * impulse;
         }
-        // The effective-mass matrix is constant over the 180 iterations, so the reciprocal determinants that
-        // b2Mat33::Solve33 / Solve22 recompute on every call are taken from the slot (same value, same bits).
-        float exx = HJ(HJ_EXX, s), eyx = HJ(HJ_EYX, s), eyy = HJ(HJ_EYY, s);
-        const float d2 = HJ(HJ_INV2, s);
-        if (limit != 0) {
-            // third row/column of the effective mass, same expressions as b2RevoluteJoint::InitVelocityConstraints
-            float ezx = -rA.y * iA - rB.y * iB, ezy = rA.x * iA + rB.x * iB, ezz = iA + iB;
-            V2 Cdot1 = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
-            float Cdot2 = wB - wA;
-            // Solve33: ex = (exx, eyx, ezx), ey = (eyx, eyy, ezy), ez = (ezx, ezy, ezz)
-            float cx = eyy * ezz - ezy * ezy, cy = ezy * ezx - eyx * ezz, cz = eyx * ezy - eyy * ezx;   // ey x ez
-            const float det = HJ(HJ_INV3, s);
-            float ix = det * (Cdot1.x * cx + Cdot1.y * cy + Cdot2 * cz);
-            // b x ez
-            float bx = Cdot1.y * ezz - Cdot2 * ezy, by = Cdot2 * ezx - Cdot1.x * ezz, bz = Cdot1.x * ezy - Cdot1.y * ezx;
-            float iy = det * (exx * bx + eyx * by + ezx * bz);
-            // ey x b
-            float ex2 = eyy * Cdot2 - ezy * Cdot1.y, ey2 = ezy * Cdot1.x - eyx * Cdot2, ez2 = eyx * Cdot1.y - eyy * Cdot1.x;
-            float iz = det * (exx * ex2 + eyx * ey2 + ezx * ez2);
-            ix = -ix; iy = -iy; iz = -iz;
-            float jz = HJ(HJ_IMPZ, s);
-            float newImpulse = jz + iz;
-            bool reduce = (limit == 1) ? (newImpulse < 0.0f) : (newImpulse > 0.0f);
-            if (reduce) {
-                V2 rhs = -Cdot1 + jz * mk(ezx, ezy);
-                float rx = d2 * (eyy * rhs.x - eyx * rhs.y), ry = d2 * (exx * rhs.y - eyx * rhs.x);
-                ix = rx; iy = ry; iz = -jz;
-                HJ(HJ_IMPX, s) += rx; HJ(HJ_IMPY, s) += ry; HJ(HJ_IMPZ, s) = 0.0f;
-            } else {
-                HJ(HJ_IMPX, s) += ix; HJ(HJ_IMPY, s) += iy; HJ(HJ_IMPZ, s) = jz + iz;
-            }
-            V2 P = mk(ix, iy);
-            vA = vA - mA * P; wA -= iA * (cross(rA, P) + iz);
-            vB = vB + mB * P; wB += iB * (cross(rB, P) + iz);
-        } else {
-            V2 Cdot = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
-            V2 nb_ = -Cdot;
-            V2 imp = mk(d2 * (eyy * nb_.x - eyx * nb_.y), d2 * (exx * nb_.y - eyx * nb_.x));
-            HJ(HJ_IMPX, s) += imp.x; HJ(HJ_IMPY, s) += imp.y;
-            vA = vA - mA * imp; wA -= iA * cross(rA, imp);
-            vB = vB + mB * imp; wB += iB * cross(rB, imp);
-        }
-        HB(HB_VX, a) = vA.x; HB(HB_VY, a) = vA.y; HB(HB_W, a) = wA;
-        HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+        // relative velocity of the anchor points: the same expression in both Box2D paths
+        const V2 Cdot1 = vB + cross_sv(wB, rB) - vA - cross_sv(wA, rA);
+        // ---- candidate 1: point-to-point constraint only (limit inactive), Solve22(-Cdot)
+        const V2 nb_ = -Cdot1;
+        const V2 imp2 = mk(d2 * (eyy * nb_.x - eyx * nb_.y), d2 * (exx * nb_.y - eyx * nb_.x));
+        const V2 vA2 = vA - mA * imp2; const float wA2 = wA - iA * cross(rA, imp2);
+        const V2 vB2 = vB + mB * imp2; const float wB2 = wB + iB * cross(rB, imp2);
+        // ---- candidate 2: point + angular limit, Solve33 and, if the limit impulse changes sign, the reduced Solve22
+        const float ezx = -rA.y * iA - rB.y * iB, ezy = rA.x * iA + rB.x * iB, ezz = iA + iB;
+        const float Cdot2 = wB - wA;
+        const float cx = eyy * ezz - ezy * ezy, cy = ezy * ezx - eyx * ezz, cz = eyx * ezy - eyy * ezx;   // ey x ez
+        float ix = det * (Cdot1.x * cx + Cdot1.y * cy + Cdot2 * cz);
+        const float bx = Cdot1.y * ezz - Cdot2 * ezy, by = Cdot2 * ezx - Cdot1.x * ezz, bz = Cdot1.x * ezy - Cdot1.y * ezx;   // b x ez
+        float iy = det * (exx * bx + eyx * by + ezx * bz);
+        const float ex2 = eyy * Cdot2 - ezy * Cdot1.y, ey2 = ezy * Cdot1.x - eyx * Cdot2, ez2 = eyx * Cdot1.y - eyy * Cdot1.x;   // ey x b
+        float iz = det * (exx * ex2 + eyx * ey2 + ezx * ez2);
+        ix = -ix; iy = -iy; iz = -iz;
+        const float newImpulse = jz + iz;
+        const bool reduce = (limit == 1) ? (newImpulse < 0.0f) : (newImpulse > 0.0f);
+        const V2 rhs = -Cdot1 + jz * mk(ezx, ezy);
+        const float rx = d2 * (eyy * rhs.x - eyx * rhs.y), ry = d2 * (exx * rhs.y - eyx * rhs.x);
+        const float px = reduce ? rx : ix, py = reduce ? ry : iy, pz = reduce ? -jz : iz;
+        const V2 P = mk(px, py);
+        const V2 vA3 = vA - mA * P; const float wA3 = wA - iA * (cross(rA, P) + pz);
+        const V2 vB3 = vB + mB * P; const float wB3 = wB + iB * (cross(rB, P) + pz);
+        const float jz3 = reduce ? 0.0f : jz + iz;
+        // ---- select
+        const bool act = limit != 0;
+        HJ(HJ_IMPX, s) = jx + (act ? px : imp2.x);
+        HJ(HJ_IMPY, s) = jy + (act ? py : imp2.y);
+        if (act) HJ(HJ_IMPZ, s) = jz3;
+        HB(HB_VX, a) = act ? vA3.x : vA2.x; HB(HB_VY, a) = act ? vA3.y : vA2.y; HB(HB_W, a) = act ? wA3 : wA2;
+        HB(HB_VX, b) = act ? vB3.x : vB2.x; HB(HB_VY, b) = act ? vB3.y : vB2.y; HB(HB_W, b) = act ? wB3 : wB2;
     }
     __device__ __forceinline__ bool joint_solve_position(int s) {
         int meta = HJi(PJ_META, s);
