@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(32) reset_kernel(float* state, const int* __re
 // the queue drains, instead of idling until the longest-lived creature of a fixed batch dies; and the cold
 // state of the few hundred resident warps stays L2-resident.
 template <int NB, int NC, int NT>
-__global__ void __launch_bounds__(32) episode_kernel(float* slots, const int* __restrict__ order, int n_order, int* queue,
+__global__ void __launch_bounds__(32, 1) episode_kernel(float* slots, const int* __restrict__ order, int n_order, int* queue,
                                                      DevPop p, const Terrain* __restrict__ ter, const Consts* __restrict__ k,
                                                      int max_ticks, double* fitness, int* ticks, int* alive, int* status,
                                                      unsigned long long* counters) {
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32) episode_kernel(float* slots, const int* __
 
 // One warp per batch of 32 creatures; each lane advances its creature by up to n_ticks ticks.
 template <int NB, int NC, int NT>
-__global__ void __launch_bounds__(32) step_kernel(float* state, int n_ticks, const Terrain* __restrict__ ter,
+__global__ void __launch_bounds__(32, 1) step_kernel(float* state, int n_ticks, const Terrain* __restrict__ ter,
                                                   const Consts* __restrict__ k, unsigned long long* counters) {
     using SimT = Sim<NB, NC, NT>;
     extern __shared__ float hot[];

@@ -114,6 +114,7 @@ struct ClassState {
     bool active = false, pending = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t t_begin = nullptr, t_end = nullptr;     // per-class timeline of the last rem2d_run_episodes (diagnostics)
 };
 
 struct rem2d_handle {
@@ -231,6 +232,7 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
     for (auto& c : h->cls) {
         if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+        cudaEventCreate(&c.t_begin); cudaEventCreate(&c.t_end);
     }
     cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -614,8 +616,10 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
         CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
+        CK(cudaEventRecord(cs.t_begin, cs.stream));
         g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
                              h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+        CK(cudaEventRecord(cs.t_end, cs.stream));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -765,6 +769,23 @@ int rem2d_measure_fp32_peak(rem2d_handle* h, double* gflops) {
     cudaFree(d);
     *gflops = best;
     return REM2D_OK;
+}
+
+// Diagnostics: per capacity class, [nb, members, resident warps, kernel begin ms, kernel end ms] of the last
+// rem2d_run_episodes (refill mode), times relative to its start. out has room for 5 * 16 floats; returns #classes.
+int rem2d_debug_class_timeline(rem2d_handle* h, float* out) {
+    if (!h || !out) return REM2D_E_INVALID;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < N_CLASSES; ++k) {
+        ClassState& cs = h->cls[k];
+        float b = -1.0f, e = -1.0f;
+        if (cs.n_batches) { cudaEventElapsedTime(&b, h->ev_start, cs.t_begin); cudaEventElapsedTime(&e, h->ev_start, cs.t_end); }
+        out[5 * k] = (float)g_classes(k).nb; out[5 * k + 1] = (float)cs.n_members; out[5 * k + 2] = (float)cs.episode_grid;
+        out[5 * k + 3] = b; out[5 * k + 4] = e;
+    }
+    cudaGetLastError();
+    return N_CLASSES;
 }
 
 float rem2d_last_step_ms(rem2d_handle* h) { return h ? h->last_ms : 0.0f; }

@@ -896,23 +896,17 @@ struct Sim {
         V2 cA = mk(HB(HB_VX, a), HB(HB_VY, a)); float aA = HB(HB_W, a);
         V2 cB = mk(HB(HB_VX, b), HB(HB_VY, b)); float aB = HB(HB_W, b);
         float angularError = 0.0f, positionError = 0.0f;
-        if (limit != 0) {
-            float motorMass = iA + iB;
-            if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
-            float angle = aB - aA - 0.0f;
-            float limitImpulse = 0.0f;
-            if (limit == 1) {
-                float Cc = angle - HJ(PJ_LOWER, s);
-                angularError = -Cc;
-                Cc = clampf(Cc + RB_ANGULAR_SLOP, -RB_MAX_ANG_CORR, 0.0f);
-                limitImpulse = -motorMass * Cc;
-            } else {
-                float Cc = angle - HJ(PJ_UPPER, s);
-                angularError = Cc;
-                Cc = clampf(Cc - RB_ANGULAR_SLOP, 0.0f, RB_MAX_ANG_CORR);
-                limitImpulse = -motorMass * Cc;
-            }
-            aA -= iA * limitImpulse; aB += iB * limitImpulse;
+        {   // angular limit, evaluated for every lane and selected (lanes disagree on the limit state)
+            const float motorMass = HJ(HJ_MMASS, s);      // 1 / (iA + iB): this slot survives the position overlay
+            const float angle = aB - aA - 0.0f;
+            const float Cl = angle - HJ(PJ_LOWER, s), Cu = angle - HJ(PJ_UPPER, s);
+            const float Ccl = clampf(Cl + RB_ANGULAR_SLOP, -RB_MAX_ANG_CORR, 0.0f);
+            const float Ccu = clampf(Cu - RB_ANGULAR_SLOP, 0.0f, RB_MAX_ANG_CORR);
+            const float limitImpulse = -motorMass * (limit == 1 ? Ccl : Ccu);
+            const float aA1 = aA - iA * limitImpulse, aB1 = aB + iB * limitImpulse;
+            const bool act = limit != 0;
+            angularError = act ? (limit == 1 ? -Cl : Cu) : 0.0f;
+            aA = act ? aA1 : aA; aB = act ? aB1 : aB;
         }
         Rot qA = rot_set(aA), qB = rot_set(aB);
         V2 rA = rmul(qA, mk(HJ(PJ_LAAX, s), HJ(PJ_LAAY, s)) - mk(0.0f, 0.0f));

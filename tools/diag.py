@@ -15,6 +15,15 @@ fit, ticks = e.evaluate(pop, 10000)
 fit, ticks = e.evaluate(pop, 10000)
 print("episode ms", e.last_step_ms(), "steps", ticks.sum(), "rate", ticks.sum() / e.last_step_ms() * 1e3)
 print("ticks pct", np.percentile(ticks, [0, 50, 90, 99, 99.9, 100]).tolist())
+import ctypes
+buf = (ctypes.c_float * 80)()
+e.lib.rem2d_debug_class_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+ncls = e.lib.rem2d_debug_class_timeline(e.h, buf)
+for k in range(ncls):
+    if buf[5 * k + 1] > 0:
+        print("class NB=%2d members=%6d warps=%4d begin %8.1f ms end %8.1f ms" % tuple(buf[5 * k + i] for i in range(5)))
+if len(sys.argv) > 2 and sys.argv[2] == "timeline":
+    sys.exit(0)
 nb = np.diff(pop.body_off)
 print("nb hist", np.bincount(nb).tolist())
 for lo, hi in ((1, 2), (3, 4), (5, 8), (9, 12), (13, 16), (17, 22)):
