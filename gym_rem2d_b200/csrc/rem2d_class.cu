@@ -22,7 +22,8 @@ template <int NB, int NC, int NT>
 __global__ void __launch_bounds__(32, 1) episode_kernel(float* slots, const int* __restrict__ order, int n_order, int* queue,
                                                      DevPop p, const Terrain* __restrict__ ter, const Consts* __restrict__ k,
                                                      int max_ticks, double* fitness, int* ticks, int* alive, int* status,
-                                                     unsigned long long* counters) {
+                                                     unsigned long long* counters, int park_ticks, float* park_state,
+                                                     int* park_creature, int* park_count) {
     using SimT = Sim<NB, NC, NT>;
     extern __shared__ float hot[];
     const int lane = threadIdx.x;
@@ -50,6 +51,13 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(float* slots, const int*
                 // a creature that outgrew a capacity of this class is re-run by the host in the next class up:
                 // its partial work must not be counted
                 if (st) sim.cnt = snapshot;
+                my = -1;
+            } else if (park_ticks > 0 && t >= park_ticks) {
+                // long-lived creature: park its state; the latency-oriented tail kernel (one warp per creature) finishes it
+                const int slot = atomicAdd(park_count, 1);
+                float* dst = park_state + (size_t)(slot >> 5) * SimT::WORDS * 32 + (slot & 31);
+                for (int w = 0; w < SimT::WORDS; ++w) dst[w * 32] = sim.g[w * 32];
+                park_creature[slot] = my;
                 my = -1;
             }
         }
@@ -91,6 +99,58 @@ __global__ void __launch_bounds__(32, 1) step_kernel(float* state, int n_ticks, 
 }
 
 
+// Tail kernel: ONE WARP PER CREATURE for the few long-lived creatures that bound the makespan. Lane 0 runs the scalar
+// parts of the tick on the creature's parked column; all 32 lanes share the 180 velocity iterations as a bit-identical
+// dependency wavefront (Sim::wavefront_velocity), which cuts the per-tick latency of a large creature several times.
+template <int NB, int NC, int NT>
+__global__ void __launch_bounds__(32, 1) tail_kernel(float* park_state, const int* __restrict__ park_creature, int n_parked,
+                                                     const Terrain* __restrict__ ter, const Consts* __restrict__ k, int max_ticks,
+                                                     double* fitness, int* ticks, int* alive, int* status,
+                                                     unsigned long long* counters) {
+    using SimT = Sim<NB, NC, NT, 1>;
+    __shared__ float hot[SimT::HOT_WORDS];
+    __shared__ int ver[NB];
+    const int lane = threadIdx.x, slot = blockIdx.x;
+    if (slot >= n_parked) return;
+    SimT sim;
+    sim.g = park_state + (size_t)(slot >> 5) * SimT::WORDS * 32 + (slot & 31);
+    sim.h = hot;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
+    for (;;) {
+        int nt = 0, solved = 0;
+        if (lane == 0) solved = sim.tick_pre(nt) ? 1 : 0;
+        solved = __shfl_sync(0xffffffffu, solved, 0);
+        nt = __shfl_sync(0xffffffffu, nt, 0);
+        __syncwarp();
+        if (solved) {
+            if (sim.nj + nt <= 64) sim.wavefront_velocity(nt, ver, lane);
+            else if (lane == 0) sim.solve_velocity(nt);
+        }
+        __syncwarp();
+        int done = 0;
+        if (lane == 0) {
+            sim.tick_post(solved != 0, nt);
+            const int t = sim.Si(S_TICKS), st = sim.Si(S_STATUS);
+            if (!sim.Si(S_ALIVE) || t >= max_ticks || st) {
+                const int my = park_creature[slot];
+                fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = st;
+                done = 1;
+            }
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done) break;
+    }
+    if (lane == 0) {
+        const int st = sim.Si(S_STATUS);
+        if (!st)
+            for (int i = 0; i < REM2D_N_COUNTERS; ++i)
+                if (sim.cnt.c[i]) atomicAdd(&counters[i], (unsigned long long)sim.cnt.c[i]);
+    }
+}
+
 #define X(i, NB_, NC_, NT_) \
     constexpr int kNB_##i = NB_, kNC_##i = NC_, kNT_##i = NT_;
 REM2D_CLASSES(X)
@@ -114,10 +174,17 @@ static void launch_step(int grid, cudaStream_t st, float* state, int n_ticks, co
 }
 static void launch_episode(int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue, DevPop p,
                            const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
-                           unsigned long long* counters) {
+                           unsigned long long* counters, int park_ticks, float* park_state, int* park_creature, int* park_count) {
     episode_kernel<kNB, kNC, kNT><<<grid, 32, SimK::HOT_WORDS * 128, st>>>(slots, order, n_order, queue, p, ter, k, max_ticks,
-                                                                            fitness, ticks, alive, status, counters);
+                                                                            fitness, ticks, alive, status, counters, park_ticks,
+                                                                            park_state, park_creature, park_count);
+}
+static void launch_tail(int grid, cudaStream_t st, float* park_state, const int* park_creature, int n_parked, const Terrain* ter,
+                        const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
+                        unsigned long long* counters) {
+    tail_kernel<kNB, kNC, kNT><<<grid, 32, 0, st>>>(park_state, park_creature, n_parked, ter, k, max_ticks, fitness, ticks, alive,
+                                                    status, counters);
 }
 extern const ClassOps CAT(rem2d_class_ops_, REM2D_CLASS_ID) = {
     kNB, kNC, kNT, SimK::NJ, SimK::OFF_BODY, SimK::OFF_JOINT, SimK::OFF_CONT, SimK::OFF_EDGE, SimK::WORDS, SimK::HOT_WORDS,
-    set_attributes, launch_reset, launch_step, launch_episode };
+    set_attributes, launch_reset, launch_step, launch_episode, launch_tail };

@@ -514,7 +514,7 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
             CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
             g_classes(k).episode(batches, h->user_stream, d_slots, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter, h->d_consts,
-                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, 0, nullptr, nullptr, nullptr);
             h->launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->user_stream));
@@ -608,6 +608,9 @@ static int launch_phased(rem2d_handle* h, int max_ticks) {
 // Whole episodes for the uploaded population on the persistent episode kernels (one per class, concurrent).
 static int launch_episodes(rem2d_handle* h, int max_ticks) {
     if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
+    // creatures still alive after park_ticks are finished by the tail kernel (REM2D_PARK_TICKS=0 disables parking)
+    int park_ticks = 192;
+    if (const char* e = getenv("REM2D_PARK_TICKS")) park_ticks = atoi(e);
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
     CK(cudaEventRecord(h->ev_start, h->user_stream));
     int rc = fork_streams(h);
@@ -617,12 +620,38 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         if (!cs.n_batches) continue;
         CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
         CK(cudaEventRecord(cs.t_begin, cs.stream));
+        CK(cudaMemsetAsync(cs.d_n_alive, 0, sizeof(int), cs.stream));
         g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
-                             h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+                             h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
+                             park_ticks < max_ticks ? park_ticks : 0, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive);
+        CK(cudaMemcpyAsync(cs.h_n_alive, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, cs.stream));
         CK(cudaEventRecord(cs.t_end, cs.stream));
         h->launches++;
     }
     CK(cudaGetLastError());
+    if (park_ticks > 0 && park_ticks < max_ticks) {
+        // tail: as soon as a class's episode kernel is done, its parked creatures go to the warp-per-creature kernel
+        int waiting = 0;
+        bool pend[N_CLASSES];
+        for (int k = 0; k < N_CLASSES; ++k) { pend[k] = h->cls[k].n_batches > 0; waiting += pend[k] ? 1 : 0; }
+        while (waiting > 0) {
+            for (int k = N_CLASSES - 1; k >= 0; --k) {
+                if (!pend[k]) continue;
+                ClassState& cs = h->cls[k];
+                cudaError_t q = cudaStreamQuery(cs.stream);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) { h->err = std::string("episode kernel: ") + cudaGetErrorString(q); return REM2D_E_CUDA; }
+                pend[k] = false; --waiting;
+                const int parked = *cs.h_n_alive;
+                if (parked > 0) {
+                    g_classes(k).tail(parked, cs.stream, cs.d_state2, cs.d_lc_work[0], parked, h->d_ter, h->d_consts, max_ticks,
+                                      h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+                    h->launches++;
+                    CK(cudaGetLastError());
+                }
+            }
+        }
+    }
     rc = join_streams(h);
     if (rc) return rc;
     rc = promote_overflowed(h, max_ticks);

@@ -193,7 +193,9 @@ struct DevPop {
 // work counters kept in registers and flushed once per launch
 struct Cnt { unsigned int c[REM2D_N_COUNTERS]; };   // per lane per launch; summed into 64-bit totals
 
-template <int NB, int NC, int NT>
+// HS = lane stride of the hot (shared memory) block: 32 when a warp holds 32 creatures (bank == lane), 1 when a whole
+// warp works on one creature (tail kernel).
+template <int NB, int NC, int NT, int HS = 32>
 struct Sim {
     static constexpr int NJ = NB - 1 > 0 ? NB - 1 : 1;
     static constexpr int OFF_BODY = S_COUNT;
@@ -232,20 +234,20 @@ struct Sim {
     __device__ __forceinline__ int Ci(int f, int c) { return __float_as_int(C(f, c)); }
     __device__ __forceinline__ void setCi(int f, int c, int v) { C(f, c) = __int_as_float(v); }
     __device__ __forceinline__ float& EA(int e) { return g[(OFF_EDGE + e) * 32]; }
-    __device__ __forceinline__ float& HB(int f, int i) { return h[(f * NB + i) * 32]; }
-    __device__ __forceinline__ float& HJ(int f, int j) { return h[(HOFF_JOINT + f * NJ + j) * 32]; }
+    __device__ __forceinline__ float& HB(int f, int i) { return h[(f * NB + i) * HS]; }
+    __device__ __forceinline__ float& HJ(int f, int j) { return h[(HOFF_JOINT + f * NJ + j) * HS]; }
     __device__ __forceinline__ int HJi(int f, int j) { return __float_as_int(HJ(f, j)); }
     // Hot contact slot t: shared memory for t < NT, a spill region of the cold block otherwise. The two
     // call sites of for_contacts() are specialised by the compiler (LDS/STS vs LDG/STG).
     template <class F>
     __device__ __forceinline__ void for_contacts(int nt, F f) {
         const int n1 = nt < NT ? nt : NT;
-        for (int t = 0; t < n1; ++t) f(h + (HOFF_CONT + t) * 32, NT * 32, t);
+        for (int t = 0; t < n1; ++t) f(h + (HOFF_CONT + t) * HS, NT * HS, t);
         for (int t = NT; t < nt; ++t) f(g + (OFF_SPILL + (t - NT)) * 32, NS * 32, t);
     }
     template <class F>
     __device__ __forceinline__ void with_contact(int t, F f) {
-        if (t < NT) f(h + (HOFF_CONT + t) * 32, NT * 32);
+        if (t < NT) f(h + (HOFF_CONT + t) * HS, NT * HS);
         else f(g + (OFF_SPILL + (t - NT)) * 32, NS * 32);
     }
 
@@ -927,13 +929,17 @@ struct Sim {
     }
 
     // ---- b2World::Solve for the creature's single island (+ SynchronizeFixtures + FindNewContacts)
-    __device__ void solve(float dtRatio) {
+    // solve_pre: integrate velocities, stage + warm start the constraints; returns false if the island sleeps.
+    // solve_velocity: the 180 sequential-impulse iterations. solve_post: store impulses, integrate positions, position
+    // iterations, sleeping, SynchronizeFixtures + FindNewContacts.
+    __device__ bool solve_pre(float dtRatio, int& nt_out) {
         const float hdt = k->dt;
+        nt_out = 0;
         // a creature is one island (tree of joints); it is solved iff its seed body is awake. Jointed
         // creatures are always awake here (the motor-speed setter woke them); a lone body may sleep.
         bool anyAwake = false;
         for (int b = 0; b < nb; ++b) anyAwake |= (Bi(BF_FLAGS, b) & BFL_AWAKE) != 0;
-        if (!anyAwake) return;
+        if (!anyAwake) return false;
         for (int b = 0; b < nb; ++b) {
             set_awake(b, true);
             float cx = B(BF_CX, b), cy = B(BF_CY, b), a = B(BF_A, b);
@@ -1031,13 +1037,21 @@ struct Sim {
             HJ(HJ_MSPEED, s) = J(JF_MSPEED, j);
             HJ(HJ_MAXIMP, s) = hdt * J(JF_MAXT, j);
         }
-        // ---------------- velocity iterations: the hot loop (everything in shared memory)
-        // NB: equal limits (|upper-lower| < 2*angularSlop) do not occur: limits are -+pi/2 (module_utility.py:28-29)
+        nt_out = nt;
+        return true;
+    }
+    // ---------------- velocity iterations: the hot loop (everything in shared memory)
+    // NB: equal limits (|upper-lower| < 2*angularSlop) do not occur: limits are -+pi/2 (module_utility.py:28-29)
+    __device__ void solve_velocity(int nt) {
         const int vit = k->vel_iters;
         for (int it = 0; it < vit; ++it) {
             for (int s = 0; s < nj; ++s) joint_solve_velocity(s);
             for_contacts(nt, [&](float* hc, const int st, int) { contact_solve_velocity(hc, st); });
         }
+    }
+    __device__ void solve_post(int nt) {
+        const float hdt = k->dt;
+        const int vit = k->vel_iters;
         cnt.c[REM2D_CNT_JOINT_VSOLVES] += (unsigned)(vit * nj);
         count_contact_solves(nt, vit);
         // store impulses
@@ -1481,20 +1495,10 @@ struct Sim {
         }
     }
 
-    // ---- b2World::Step
-    __device__ void world_step() {
-        const float dt = k->dt;
-        if (Si(S_NEWFIX)) { find_new_contacts(); setSi(S_NEWFIX, 0); }
-        float inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
-        float dtRatio = S(S_INVDT0) * dt;
-        collide();
-        if (dt > 0.0f) solve(dtRatio);
-        if (k->continuous && dt > 0.0f) solve_toi();
-        if (dt > 0.0f) S(S_INVDT0) = inv_dt;
-    }
-
-    // ---- Modular2D.step + the body of evaluate()'s loop
-    __device__ void tick() {
+    // ---- Modular2D.step + the body of evaluate()'s loop, in three parts so that a whole warp can take over the velocity
+    // iterations of one creature (tail kernel): tick_pre -> [solve_velocity | wavefront_velocity] -> tick_post.
+    // b2World::Step = FindNewContacts (first step) -> Collide -> Solve -> SolveTOI.
+    __device__ bool tick_pre(int& nt) {
         double wod = Sd(S_WOD_LO) + k->wod_speed;
         setSd(S_WOD_LO, wod);
         for (int j = 0; j < nj; ++j) {
@@ -1509,11 +1513,23 @@ struct Sim {
             set_awake(a, true); set_awake(b, true);
             J(JF_MSPEED, j) = (float)speed;
         }
-        world_step();
+        const float dt = k->dt;
+        if (Si(S_NEWFIX)) { find_new_contacts(); setSi(S_NEWFIX, 0); }
+        float dtRatio = S(S_INVDT0) * dt;
+        collide();
+        nt = 0;
+        return dt > 0.0f ? solve_pre(dtRatio, nt) : false;
+    }
+    __device__ void tick_post(bool solved, int nt) {
+        const float dt = k->dt;
+        if (solved) solve_post(nt);
+        if (k->continuous && dt > 0.0f) solve_toi();
+        if (dt > 0.0f) S(S_INVDT0) = 1.0f / dt;
         cnt.c[REM2D_CNT_TICKS]++;
         int i = Si(S_TICKS);
         setSi(S_TICKS, i + 1);
         float x = B(BF_CX, 0);
+        double wod = Sd(S_WOD_LO);
         double reward = (double)x;
         if (k->terminate) {
             if (x < 0.0f) reward = -100.0;
@@ -1526,6 +1542,67 @@ struct Sim {
             } else if (reward > 0.0) setSd(S_FIT_LO, reward);
             if (i + 1 >= k->evaluation_steps) setSi(S_ALIVE, 0);
         } else if (reward > 0.0) setSd(S_FIT_LO, reward);
+    }
+    __device__ void tick() {
+        int nt;
+        bool solved = tick_pre(nt);
+        if (solved) solve_velocity(nt);
+        tick_post(solved, nt);
+    }
+
+    // ---- velocity iterations of ONE creature by a whole warp (tail kernel): a dependency-respecting wavefront.
+    // Box2D's sequential order within an iteration is: joints in island order, then contacts (newest first); two
+    // constraints commute exactly iff they share no body. Lane l owns constraints l and l+32 of that sequence; a per-body
+    // version counter says how many solves have been applied to the body, and a constraint of iteration `it` may run as
+    // soon as each of its bodies has version it * degree(body) + rank(constraint within the body's sequence). Every
+    // solve therefore reads exactly the velocities it would read in the sequential order — results are bit-identical —
+    // while independent constraints, also of consecutive iterations, run concurrently in different lanes.
+    // `ver` is NB ints of shared memory. Must be called by all 32 lanes.
+    __device__ void wavefront_velocity(int nt, int* ver, int lane) {
+        const int n = nj + nt;
+        const int vit = k->vel_iters;
+        for (int b = lane; b < nb; b += 32) ver[b] = 0;
+        // owned constraints: c0 = lane, c1 = lane + 32 (n <= 64 is guaranteed by the capacity classes: NJ <= 43, nt <= ...)
+        int cA[2], cB[2], rkA[2], rkB[2], dgA[2], dgB[2];
+        int nown = 0;
+        for (int q = 0; q < 2; ++q) {
+            int c = lane + 32 * q;
+            cA[q] = cB[q] = -1; rkA[q] = rkB[q] = dgA[q] = dgB[q] = 0;
+            if (c >= n) continue;
+            nown = q + 1;
+            if (c < nj) { int meta = HJi(HJ_META, c); cA[q] = meta & 0xff; cB[q] = (meta >> 8) & 0xff; }
+            else with_contact(c - nj, [&](float* hc, const int st) { cB[q] = __float_as_int(hc[HC_META * st]) & 0xff; });
+            for (int c2 = 0; c2 < n; ++c2) {
+                int a2 = -1, b2 = -1;
+                if (c2 < nj) { int meta = HJi(HJ_META, c2); a2 = meta & 0xff; b2 = (meta >> 8) & 0xff; }
+                else with_contact(c2 - nj, [&](float* hc, const int st) { b2 = __float_as_int(hc[HC_META * st]) & 0xff; });
+                if (cA[q] >= 0 && (a2 == cA[q] || b2 == cA[q])) { ++dgA[q]; if (c2 < c) ++rkA[q]; }
+                if (a2 == cB[q] || b2 == cB[q]) { ++dgB[q]; if (c2 < c) ++rkB[q]; }
+            }
+        }
+        __syncwarp();
+        int it = 0, q = 0;                 // next owned constraint to run: (iteration it, slot q)
+        const int total = n;
+        (void)total;
+        for (;;) {
+            bool finished = (nown == 0) || (it >= vit);
+            bool ready = false;
+            if (!finished) {
+                ready = ver[cB[q]] == it * dgB[q] + rkB[q];
+                if (cA[q] >= 0) ready = ready && (ver[cA[q]] == it * dgA[q] + rkA[q]);
+            }
+            if (__all_sync(0xffffffffu, finished)) break;
+            __syncwarp();                   // everybody has read the versions of this pass
+            if (ready) {
+                int c = lane + 32 * q;
+                if (c < nj) joint_solve_velocity(c);
+                else with_contact(c - nj, [&](float* hc, const int st) { contact_solve_velocity(hc, st); });
+                if (cA[q] >= 0) ver[cA[q]] += 1;
+                ver[cB[q]] += 1;
+                if (++q == nown) { q = 0; ++it; }
+            }
+            __syncwarp();                   // velocity and version writes are visible before the next pass
+        }
     }
 };
 
