@@ -10,6 +10,10 @@ import os
 
 import numpy as np
 
+# The library runs one stream per capacity class (+ one per tail kernel); with the default 8 hardware queues, streams
+# alias and stream-waits block unrelated launches. Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB = os.environ.get("REM2D_CUDA_LIB") or os.path.join(HERE, "csrc", "librem2d_cuda.so")   # env override: A/B builds
 

@@ -163,7 +163,16 @@ using SimK = Sim<kNB, kNC, kNT>;
 static cudaError_t set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(step_kernel<kNB, kNC, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SimK::HOT_WORDS * 128);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(episode_kernel<kNB, kNC, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SimK::HOT_WORDS * 128);
+    e = cudaFuncSetAttribute(episode_kernel<kNB, kNC, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SimK::HOT_WORDS * 128);
+    if (e != cudaSuccess) return e;
+    // All kernels that can be resident together should agree on the shared-memory carve-out of the SM: a small-smem kernel
+    // (tail) would otherwise pin its SMs in a large-L1 configuration and lock the big episode CTAs of other classes out
+    // (measured: 1.4x slower whole run when a tail kernel was resident next to the episode kernels).
+    e = cudaFuncSetAttribute(step_kernel<kNB, kNC, kNT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(episode_kernel<kNB, kNC, kNT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tail_kernel<kNB, kNC, kNT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 static void launch_reset(int grid, cudaStream_t st, float* state, const int* lane_creature, DevPop p) {
     reset_kernel<kNB, kNC, kNT><<<grid, 32, 0, st>>>(state, lane_creature, p);
