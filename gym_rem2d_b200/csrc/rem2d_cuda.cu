@@ -408,18 +408,22 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         bool fixed[N_CLASSES];
         for (int k = 0; k < N_CLASSES; ++k) {
             work[k] = 0.0; fixed[k] = members[k].empty(); smem[k] = g_classes(k).hot_words * 128.0 + 1024.0;
-            for (int c : members[k]) work[k] += 1.0 + (pop->body_off[c + 1] - pop->body_off[c]);
+            // per-creature cost ~ tick latency of its size: measured ~0.3 ms + 0.085 ms per body for a resident warp; lone
+            // bodies fall asleep after landing and cost almost nothing
+            for (int c : members[k]) { int nbc = pop->body_off[c + 1] - pop->body_off[c]; work[k] += nbc == 1 ? 1.0 : 3.5 + nbc; }
             h->cls[k].episode_grid = 0;
         }
+        // warps_k = W * work_k with W such that sum_k warps_k * smem_k = budget: every class then needs about the same
+        // number of sequential creature-lifetimes per lane times its own tick latency, i.e. the classes finish together
         for (int round = 0; round < N_CLASSES; ++round) {
-            double wsum = 0.0;
-            for (int k = 0; k < N_CLASSES; ++k) if (!fixed[k]) wsum += work[k];
-            if (wsum <= 0.0) break;
+            double denom = 0.0;
+            for (int k = 0; k < N_CLASSES; ++k) if (!fixed[k]) denom += work[k] * smem[k];
+            if (denom <= 0.0) break;
+            const double W = budget / denom;
             bool changed = false;
             for (int k = 0; k < N_CLASSES; ++k) {
                 if (fixed[k]) continue;
-                int want = (int)(budget * work[k] / wsum / smem[k]);
-                if (want >= h->cls[k].n_batches) {        // the class fits entirely: fix it and give the rest back
+                if ((int)(W * work[k]) >= h->cls[k].n_batches) {        // the class fits entirely: fix it and give the rest back
                     h->cls[k].episode_grid = h->cls[k].n_batches;
                     budget -= h->cls[k].n_batches * smem[k];
                     fixed[k] = true; changed = true;
@@ -427,7 +431,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
             }
             if (!changed) {
                 for (int k = 0; k < N_CLASSES; ++k)
-                    if (!fixed[k]) h->cls[k].episode_grid = std::max(1, (int)(budget * work[k] / wsum / smem[k]));
+                    if (!fixed[k]) h->cls[k].episode_grid = std::max(1, (int)(W * work[k]));
                 break;
             }
         }
