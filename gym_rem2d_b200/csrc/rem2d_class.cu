@@ -22,8 +22,8 @@ template <int NB, int NC, int NT>
 __global__ void __launch_bounds__(32, 1) episode_kernel(float* slots, const int* __restrict__ order, int n_order, int* queue,
                                                      DevPop p, const Terrain* __restrict__ ter, const Consts* __restrict__ k,
                                                      int max_ticks, double* fitness, int* ticks, int* alive, int* status,
-                                                     unsigned long long* counters, int park_ticks, float* park_state,
-                                                     int* park_creature, int* park_count) {
+                                                     unsigned long long* counters, int park_ticks, int park_cap,
+                                                     float* park_state, int* park_creature, int* park_count) {
     using SimT = Sim<NB, NC, NT>;
     extern __shared__ float hot[];
     const int lane = threadIdx.x;
@@ -52,12 +52,22 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(float* slots, const int*
                 // its partial work must not be counted
                 if (st) sim.cnt = snapshot;
                 my = -1;
-            } else if (park_ticks > 0 && t >= park_ticks) {
-                // long-lived creature: park its state; the latency-oriented tail kernel (one warp per creature) finishes it
-                const int slot = atomicAdd(park_count, 1);
+            } else if (park_ticks > 0 && t >= park_ticks && *(volatile int*)park_count < park_cap) {
+                // long-lived creature: park its state; the latency-oriented tail kernel (one warp per creature) finishes it.
+                // Only a bounded number of creatures is parked (the tail kernel trades throughput for latency): in an evolved
+                // population where most creatures live long, the rest simply continue here.
+                // (the counter never exceeds the cap: the host hands every counted slot to a tail kernel)
+                int slot = -1, seen = *(volatile int*)park_count;
+                while (seen < park_cap) {
+                    const int prev = atomicCAS(park_count, seen, seen + 1);
+                    if (prev == seen) { slot = seen; break; }
+                    seen = prev;
+                }
+                if (slot < 0) continue;
                 float* dst = park_state + (size_t)(slot >> 5) * SimT::WORDS * 32 + (slot & 31);
                 for (int w = 0; w < SimT::WORDS; ++w) dst[w * 32] = sim.g[w * 32];
-                park_creature[slot] = my;
+                __threadfence();                                 // the column is visible before the slot is published
+                atomicExch(&park_creature[slot], my + 1);        // 0 = allocated but not yet published
                 my = -1;
             }
         }
@@ -103,15 +113,24 @@ __global__ void __launch_bounds__(32, 1) step_kernel(float* state, int n_ticks, 
 // parts of the tick on the creature's parked column; all 32 lanes share the 180 velocity iterations as a bit-identical
 // dependency wavefront (Sim::wavefront_velocity), which cuts the per-tick latency of a large creature several times.
 template <int NB, int NC, int NT>
-__global__ void __launch_bounds__(32, 1) tail_kernel(float* park_state, const int* __restrict__ park_creature, int n_parked,
+__global__ void __launch_bounds__(32, 1) tail_kernel(float* park_state, int* park_creature, int first_slot, int n_parked,
                                                      const Terrain* __restrict__ ter, const Consts* __restrict__ k, int max_ticks,
                                                      double* fitness, int* ticks, int* alive, int* status,
                                                      unsigned long long* counters) {
     using SimT = Sim<NB, NC, NT, 1>;
     __shared__ float hot[SimT::HOT_WORDS];
     __shared__ int ver[NB];
-    const int lane = threadIdx.x, slot = blockIdx.x;
-    if (slot >= n_parked) return;
+    const int lane = threadIdx.x, slot = first_slot + blockIdx.x;
+    if ((int)blockIdx.x >= n_parked) return;
+    // the slot was allocated by an episode kernel that may still be running: wait until its column has been published
+    int my = -1;
+    if (lane == 0) {
+        int v;
+        while ((v = atomicAdd(&park_creature[slot], 0)) == 0) __nanosleep(500);
+        my = v - 1;
+        __threadfence();
+    }
+    my = __shfl_sync(0xffffffffu, my, 0);
     SimT sim;
     sim.g = park_state + (size_t)(slot >> 5) * SimT::WORDS * 32 + (slot & 31);
     sim.h = hot;
@@ -135,7 +154,6 @@ __global__ void __launch_bounds__(32, 1) tail_kernel(float* park_state, const in
             sim.tick_post(solved != 0, nt);
             const int t = sim.Si(S_TICKS), st = sim.Si(S_STATUS);
             if (!sim.Si(S_ALIVE) || t >= max_ticks || st) {
-                const int my = park_creature[slot];
                 fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = st;
                 done = 1;
             }
@@ -183,15 +201,16 @@ static void launch_step(int grid, cudaStream_t st, float* state, int n_ticks, co
 }
 static void launch_episode(int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue, DevPop p,
                            const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
-                           unsigned long long* counters, int park_ticks, float* park_state, int* park_creature, int* park_count) {
+                           unsigned long long* counters, int park_ticks, int park_cap, float* park_state, int* park_creature,
+                           int* park_count) {
     episode_kernel<kNB, kNC, kNT><<<grid, 32, SimK::HOT_WORDS * 128, st>>>(slots, order, n_order, queue, p, ter, k, max_ticks,
-                                                                            fitness, ticks, alive, status, counters, park_ticks,
+                                                                            fitness, ticks, alive, status, counters, park_ticks, park_cap,
                                                                             park_state, park_creature, park_count);
 }
-static void launch_tail(int grid, cudaStream_t st, float* park_state, const int* park_creature, int n_parked, const Terrain* ter,
+static void launch_tail(int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked, const Terrain* ter,
                         const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
                         unsigned long long* counters) {
-    tail_kernel<kNB, kNC, kNT><<<grid, 32, 0, st>>>(park_state, park_creature, n_parked, ter, k, max_ticks, fitness, ticks, alive,
+    tail_kernel<kNB, kNC, kNT><<<grid, 32, 0, st>>>(park_state, park_creature, first_slot, n_parked, ter, k, max_ticks, fitness, ticks, alive,
                                                     status, counters);
 }
 extern const ClassOps CAT(rem2d_class_ops_, REM2D_CLASS_ID) = {

@@ -27,9 +27,9 @@ struct ClassOps {
                  unsigned long long* counters);
     void (*episode)(int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue, rem2d::DevPop p,
                     const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks, int* alive,
-                    int* status, unsigned long long* counters, int park_ticks, float* park_state, int* park_creature,
-                    int* park_count);
-    void (*tail)(int grid, cudaStream_t st, float* park_state, const int* park_creature, int n_parked, const rem2d::Terrain* ter,
+                    int* status, unsigned long long* counters, int park_ticks, int park_cap, float* park_state,
+                    int* park_creature, int* park_count);
+    void (*tail)(int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked, const rem2d::Terrain* ter,
                  const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
                  unsigned long long* counters);
 };

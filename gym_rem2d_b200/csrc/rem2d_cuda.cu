@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -123,6 +125,10 @@ struct rem2d_handle {
     Terrain* d_ter = nullptr;
     Consts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;
+    cudaStream_t tail_pool[16] = {};     // tail kernels are launched on demand, round robin over this pool
+    cudaStream_t poll_stream = nullptr;
+    cudaEvent_t pool_done = nullptr;
+    int* h_poll = nullptr;               // pinned [N_CLASSES]
     bool have_terrain = false, have_pop = false;
     bool state_valid = false;           // per-creature state blocks hold a consistent snapshot (reset/step path)
     bool results_valid = false;         // d_fitness/d_ticks/... were written by the episode kernel
@@ -235,6 +241,10 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
         cudaEventCreate(&c.t_begin); cudaEventCreate(&c.t_end);
     }
     cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
+    for (auto& st : h->tail_pool) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->pool_done, cudaEventDisableTiming);
+    cudaMallocHost(&h->h_poll, sizeof(int) * 16);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     for (int q = 0; q < N_CLASSES; ++q)
@@ -249,6 +259,10 @@ int rem2d_destroy(rem2d_handle* h) {
     cudaDeviceSynchronize();
     free_population(h);
     for (auto& c : h->cls) { if (c.stream) cudaStreamDestroy(c.stream); if (c.done) cudaEventDestroy(c.done); }
+    for (auto& st : h->tail_pool) if (st) cudaStreamDestroy(st);
+    if (h->poll_stream) cudaStreamDestroy(h->poll_stream);
+    if (h->pool_done) cudaEventDestroy(h->pool_done);
+    if (h->h_poll) cudaFreeHost(h->h_poll);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -518,7 +532,7 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
             CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
             g_classes(k).episode(batches, h->user_stream, d_slots, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter, h->d_consts,
-                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, 0, nullptr, nullptr, nullptr);
+                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, 0, 0, nullptr, nullptr, nullptr);
             h->launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->user_stream));
@@ -625,35 +639,55 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
         CK(cudaEventRecord(cs.t_begin, cs.stream));
         CK(cudaMemsetAsync(cs.d_n_alive, 0, sizeof(int), cs.stream));
+        CK(cudaMemsetAsync(cs.d_lc_work[0], 0, cs.lane_creature.size() * sizeof(int), cs.stream));     // "unpublished" markers
         g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
                              h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                             park_ticks < max_ticks ? park_ticks : 0, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive);
+                             park_ticks < max_ticks ? park_ticks : 0, std::max(32, std::min(h->n_sms * 4, cs.n_members / 16)),
+                             cs.d_state2, cs.d_lc_work[0], cs.d_n_alive);
         CK(cudaMemcpyAsync(cs.h_n_alive, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, cs.stream));
         CK(cudaEventRecord(cs.t_end, cs.stream));
         h->launches++;
     }
     CK(cudaGetLastError());
     if (park_ticks > 0 && park_ticks < max_ticks) {
-        // tail: as soon as a class's episode kernel is done, its parked creatures go to the warp-per-creature kernel
-        int waiting = 0;
-        bool pend[N_CLASSES];
-        for (int k = 0; k < N_CLASSES; ++k) { pend[k] = h->cls[k].n_batches > 0; waiting += pend[k] ? 1 : 0; }
-        while (waiting > 0) {
-            for (int k = N_CLASSES - 1; k >= 0; --k) {
-                if (!pend[k]) continue;
-                ClassState& cs = h->cls[k];
-                cudaError_t q = cudaStreamQuery(cs.stream);
-                if (q == cudaErrorNotReady) continue;
-                if (q != cudaSuccess) { h->err = std::string("episode kernel: ") + cudaGetErrorString(q); return REM2D_E_CUDA; }
-                pend[k] = false; --waiting;
-                const int parked = *cs.h_n_alive;
-                if (parked > 0) {
-                    g_classes(k).tail(parked, cs.stream, cs.d_state2, cs.d_lc_work[0], parked, h->d_ter, h->d_consts, max_ticks,
-                                      h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
-                    h->launches++;
-                    CK(cudaGetLastError());
-                }
+        // Tail: while the episode kernels run, poll their park counters and hand newly parked creatures to the
+        // warp-per-creature tail kernel right away (pool of streams), so the sequential ticks of the longest-lived
+        // creatures overlap the bulk instead of extending the run; the last launch of a class happens when its episode
+        // kernel has finished.
+        bool running[N_CLASSES];
+        int launched[N_CLASSES];
+        int n_running = 0, rr = 0;
+        for (int k = 0; k < N_CLASSES; ++k) { running[k] = h->cls[k].n_batches > 0; launched[k] = 0; n_running += running[k] ? 1 : 0; }
+        while (n_running > 0) {
+            bool finished_now[N_CLASSES];
+            for (int k = 0; k < N_CLASSES; ++k) {
+                finished_now[k] = false;
+                if (!running[k]) continue;
+                cudaError_t q = cudaStreamQuery(h->cls[k].stream);       // BEFORE reading the counter: no slot can be missed
+                if (q == cudaSuccess) finished_now[k] = true;
+                else if (q != cudaErrorNotReady) { h->err = std::string("episode kernel: ") + cudaGetErrorString(q); return REM2D_E_CUDA; }
+                CK(cudaMemcpyAsync(&h->h_poll[k], h->cls[k].d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, h->poll_stream));
             }
+            CK(cudaStreamSynchronize(h->poll_stream));
+            for (int k = N_CLASSES - 1; k >= 0; --k) {
+                if (!running[k]) continue;
+                ClassState& cs = h->cls[k];
+                const int cnt = h->h_poll[k];
+                // early launches in chunks (a handful of creatures or whatever is there when the class is done)
+                if (cnt > launched[k] && (finished_now[k] || cnt - launched[k] >= 4)) {
+                    g_classes(k).tail(cnt - launched[k], h->tail_pool[rr++ & 15], cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
+                                      h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+                    CK(cudaGetLastError());
+                    h->launches++;
+                    launched[k] = cnt;
+                }
+                if (finished_now[k]) { running[k] = false; --n_running; }
+            }
+            if (n_running > 0) std::this_thread::sleep_for(std::chrono::microseconds(500));
+        }
+        for (auto& ts : h->tail_pool) {
+            CK(cudaEventRecord(h->pool_done, ts));
+            CK(cudaStreamWaitEvent(h->user_stream, h->pool_done, 0));
         }
     }
     rc = join_streams(h);

@@ -124,3 +124,22 @@ def test_capacity_overflow_is_promoted_to_a_larger_class():
     assert np.array_equal(tg, to) and np.array_equal(fg, fo)
     # (work counters are not compared here: aborted attempts in too-small classes are counted as work)
     assert g.counters()["ticks"] >= o.counters()["ticks"]
+
+
+def test_park_cap_and_thresholds_do_not_change_results(monkeypatch):
+    """The tail kernel (warp-per-creature wavefront) is an execution strategy: whatever the park threshold, results
+    must be identical to the oracle. A threshold of 8 ticks with 300 creatures exceeds the park cap of small classes,
+    so both the parked and the not-parked continuation are exercised."""
+    random.seed(51)
+    pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(300)])
+    xs, ys = terrain.generate_terrain()
+    o = OracleEngine(threads=8)
+    o.set_terrain(ys, K.TERRAIN_STEP)
+    fo, to = o.evaluate(pop, 400)
+    for park in ("8", "64", "0"):
+        monkeypatch.setenv("REM2D_PARK_TICKS", park)
+        g = Engine(device=0)
+        g.set_terrain(ys, K.TERRAIN_STEP)
+        fg, tg = g.evaluate(pop, 400)
+        assert np.array_equal(tg, to) and np.array_equal(fg, fo), park
+        assert g.counters() == o.counters(), park
