@@ -129,7 +129,7 @@ def main():
         if rank != 0:
             return
         xs, ys = terrain.generate_terrain()
-        sample = min(args.pop, max(256, 96 * cores))
+        sample = min(args.pop, max(256, 1800 * cores))      # ~10 s of CPU work per step on the box's cores
         pop = random_population(sample, encodings, seed=args.seed, workers=max(1, cores // 2), cache_dir=cache)
         vals = []
         for i in range(args.warmup + args.steps):
@@ -256,7 +256,7 @@ def main():
                 "counters": counters, "fitness": {"mean": float(np.mean(fit_all)), "max": float(np.max(fit_all)), "n": int(len(fit_all))},
                 "mean_ticks_per_creature": creature_steps / pop.n_creatures}
         if not args.no_cpu_baseline and world == 1:
-            sample = min(args.pop, max(256, 96 * cores))
+            sample = min(args.pop, max(256, 1800 * cores))      # ~10 s of CPU work
             v, dt, n, cs = cpu_baseline(pop, ys, sample, cores)
             line["cpu_baseline"] = {"value": v, "unit": "creature-steps/s", "cores": cores, "kind": "port",
                                     "sample": "first %d creatures of the same population, whole episodes, %.1f s; pybox2d is not "

@@ -94,6 +94,19 @@ __global__ void fp32_issue_kernel(float* out, int iters, float b, float c) {
 }
 
 // ------------------------------------------------------------------ handle
+// Device buffers are grow-only and reused across uploads: re-allocating ~1 GB of state blocks on every rem2d_evaluate
+// call cost ~0.4 s per generation.
+struct Buf { void* p = nullptr; size_t cap = 0; };
+static cudaError_t ensure(Buf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e == cudaSuccess) b.cap = want;
+    return e;
+}
+
 struct ClassState {
     std::vector<int> lane_creature;     // host copy: [n_batches*32], -1 = padding lane
     int n_batches = 0;
@@ -102,6 +115,7 @@ struct ClassState {
     float* d_state = nullptr;
     int* d_lane_creature = nullptr;
     int* d_queue = nullptr;
+    Buf b_state, b_state2, b_lc, b_lcw0, b_lcw1, b_dst, b_small;   // backing storage (grow-only)
     // phased evaluation with survivor compaction (ping-pong buffers)
     float* d_state2 = nullptr;
     int* d_lc_work[2] = {nullptr, nullptr};   // lane -> creature maps of the compacted phases (d_lane_creature stays the static map)
@@ -138,7 +152,8 @@ struct rem2d_handle {
     int n_creatures = 0, n_bodies = 0, n_joints = 0;
     std::vector<int32_t> body_off;
     std::vector<int> creature_class, creature_lane;     // lane index within the class (batch*32+lane)
-    void* d_pop_mem[16] = {};
+    Buf d_pop_mem[16];
+    Buf b_results;
     DevPop dpop{};
     ClassState cls[N_CLASSES];
     double* d_fitness = nullptr; int *d_ticks = nullptr, *d_alive = nullptr, *d_status = nullptr;
@@ -151,6 +166,8 @@ struct rem2d_handle {
 
 static thread_local std::string g_create_err;
 
+
+
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -160,27 +177,20 @@ static thread_local std::string g_create_err;
         }                                                                                                \
     } while (0)
 
-static void free_population(rem2d_handle* h) {
-    for (auto& p : h->d_pop_mem) { if (p) cudaFree(p); p = nullptr; }
-    for (auto& c : h->cls) {
-        if (c.d_state) cudaFree(c.d_state);
-        if (c.d_lane_creature) cudaFree(c.d_lane_creature);
-        if (c.d_queue) cudaFree(c.d_queue);
-        if (c.d_state2) cudaFree(c.d_state2);
-        if (c.d_lc_work[0]) cudaFree(c.d_lc_work[0]);
-        if (c.d_lc_work[1]) cudaFree(c.d_lc_work[1]);
-        if (c.d_dst_slot) cudaFree(c.d_dst_slot);
-        if (c.d_n_alive) cudaFree(c.d_n_alive);
-        if (c.h_n_alive) cudaFreeHost(c.h_n_alive);
-        c.d_state2 = nullptr; c.d_lc_work[0] = c.d_lc_work[1] = nullptr; c.d_dst_slot = nullptr; c.d_n_alive = nullptr; c.h_n_alive = nullptr;
-        c.d_state = nullptr; c.d_lane_creature = nullptr; c.d_queue = nullptr; c.n_batches = 0; c.n_members = 0; c.lane_creature.clear();
-    }
-    if (h->d_fitness) cudaFree(h->d_fitness);
-    if (h->d_ticks) cudaFree(h->d_ticks);
-    if (h->d_alive) cudaFree(h->d_alive);
-    if (h->d_status) cudaFree(h->d_status);
-    h->d_fitness = nullptr; h->d_ticks = h->d_alive = h->d_status = nullptr;
+static void free_population(rem2d_handle* h) {          // logical reset; the buffers stay allocated for reuse
+    for (auto& c : h->cls) { c.n_batches = 0; c.n_members = 0; c.lane_creature.clear(); }
     h->have_pop = false; h->state_valid = false; h->results_valid = false;
+}
+static void release_buffers(rem2d_handle* h) {
+    for (auto& b : h->d_pop_mem) { if (b.p) cudaFree(b.p); b = Buf(); }
+    for (auto& c : h->cls) {
+        Buf* bufs[] = {&c.b_state, &c.b_state2, &c.b_lc, &c.b_lcw0, &c.b_lcw1, &c.b_dst, &c.b_small};
+        for (Buf* b : bufs) { if (b->p) cudaFree(b->p); *b = Buf(); }
+        if (c.h_n_alive) cudaFreeHost(c.h_n_alive);
+        c.h_n_alive = nullptr;
+    }
+    if (h->b_results.p) cudaFree(h->b_results.p);
+    h->b_results = Buf();
 }
 
 extern "C" {
@@ -258,6 +268,7 @@ int rem2d_destroy(rem2d_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     free_population(h);
+    release_buffers(h);
     for (auto& c : h->cls) { if (c.stream) cudaStreamDestroy(c.stream); if (c.done) cudaEventDestroy(c.done); }
     for (auto& st : h->tail_pool) if (st) cudaStreamDestroy(st);
     if (h->poll_stream) cudaStreamDestroy(h->poll_stream);
@@ -306,24 +317,22 @@ int rem2d_set_terrain(rem2d_handle* h, const double* y, int32_t n, double step) 
 // joint order inside the creature's island: DFS of b2World::Solve from the newest body, each body's joint
 // list newest first. Pure topology, so it is computed once on the host.
 static void island_joint_order(int nb, const int16_t* parent, uint8_t* order) {
-    int nj = nb - 1;
+    const int nj = nb - 1;
     if (nj <= 0) return;
-    std::vector<char> bodyFlag(nb, 0), jointFlag(nj, 0);
-    std::vector<int> stack;
-    stack.push_back(nb - 1);
+    char bodyFlag[64] = {0}, jointFlag[64] = {0};      // nb <= 44 (largest capacity class)
+    int stack[64], sp = 0, n = 0;
+    stack[sp++] = nb - 1;
     bodyFlag[nb - 1] = 1;
-    int n = 0;
-    while (!stack.empty()) {
-        int b = stack.back();
-        stack.pop_back();
+    while (sp > 0) {
+        const int b = stack[--sp];
         for (int j = nj - 1; j >= 0; --j) {
             if (parent[j] != b && j + 1 != b) continue;
             if (jointFlag[j]) continue;
-            int other = parent[j] == b ? j + 1 : parent[j];
+            const int other = parent[j] == b ? j + 1 : parent[j];
             order[n++] = (uint8_t)j;
             jointFlag[j] = 1;
             if (bodyFlag[other]) continue;
-            stack.push_back(other);
+            stack[sp++] = other;
             bodyFlag[other] = 1;
         }
     }
@@ -331,10 +340,9 @@ static void island_joint_order(int nb, const int16_t* parent, uint8_t* order) {
 
 template <typename T>
 static cudaError_t upload_array(rem2d_handle* h, int slot, const T* src, size_t n, const T** dst) {
-    void* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, (n ? n : 1) * sizeof(T));
+    cudaError_t e = ensure(h->d_pop_mem[slot], (n ? n : 1) * sizeof(T));
     if (e != cudaSuccess) return e;
-    h->d_pop_mem[slot] = d;
+    void* d = h->d_pop_mem[slot].p;
     if (n) e = cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->user_stream);
     *dst = (const T*)d;
     return e;
@@ -400,18 +408,19 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         cs.n_batches = (int)((m.size() + 31) / 32);
         cs.n_members = (int)m.size();
         cs.episode_grid = cs.n_batches;     // sized below once every class is known
-        CK(cudaMalloc(&cs.d_queue, sizeof(int)));
         cs.lane_creature.assign((size_t)cs.n_batches * 32, -1);
         for (size_t i = 0; i < m.size(); ++i) { cs.lane_creature[i] = m[i]; h->creature_lane[m[i]] = (int)i; }
-        CK(cudaMalloc(&cs.d_lane_creature, cs.lane_creature.size() * sizeof(int)));
+        const size_t lane_bytes = cs.lane_creature.size() * sizeof(int);
+        const size_t state_bytes = (size_t)cs.n_batches * g_classes(k).words * 32 * sizeof(float);
+        CK(ensure(cs.b_lc, lane_bytes)); cs.d_lane_creature = (int*)cs.b_lc.p;
         CK(cudaMemcpy(cs.d_lane_creature, cs.lane_creature.data(), cs.lane_creature.size() * sizeof(int), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&cs.d_state, (size_t)cs.n_batches * g_classes(k).words * 32 * sizeof(float)));
-        CK(cudaMalloc(&cs.d_state2, (size_t)cs.n_batches * g_classes(k).words * 32 * sizeof(float)));
-        CK(cudaMalloc(&cs.d_lc_work[0], cs.lane_creature.size() * sizeof(int)));
-        CK(cudaMalloc(&cs.d_lc_work[1], cs.lane_creature.size() * sizeof(int)));
-        CK(cudaMalloc(&cs.d_dst_slot, cs.lane_creature.size() * sizeof(int)));
-        CK(cudaMalloc(&cs.d_n_alive, sizeof(int)));
-        CK(cudaMallocHost(&cs.h_n_alive, sizeof(int)));
+        CK(ensure(cs.b_state, state_bytes)); cs.d_state = (float*)cs.b_state.p;
+        CK(ensure(cs.b_state2, state_bytes)); cs.d_state2 = (float*)cs.b_state2.p;
+        CK(ensure(cs.b_lcw0, lane_bytes)); cs.d_lc_work[0] = (int*)cs.b_lcw0.p;
+        CK(ensure(cs.b_lcw1, lane_bytes)); cs.d_lc_work[1] = (int*)cs.b_lcw1.p;
+        CK(ensure(cs.b_dst, lane_bytes)); cs.d_dst_slot = (int*)cs.b_dst.p;
+        CK(ensure(cs.b_small, 64)); cs.d_n_alive = (int*)cs.b_small.p; cs.d_queue = (int*)cs.b_small.p + 4;
+        if (!cs.h_n_alive) CK(cudaMallocHost(&cs.h_n_alive, sizeof(int)));
     }
     {   // Resident warps of the persistent episode kernels. All classes run concurrently, so the shared memory of the SMs
         // (227 KB each) is divided among them in proportion to their work (bodies to simulate); a class never gets more
@@ -452,10 +461,14 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         for (int k = 0; k < N_CLASSES; ++k)
             if (h->cls[k].n_batches && h->cls[k].episode_grid < 1) h->cls[k].episode_grid = 1;
     }
-    CK(cudaMalloc(&h->d_fitness, sizeof(double) * std::max(n, 1)));
-    CK(cudaMalloc(&h->d_ticks, sizeof(int) * std::max(n, 1)));
-    CK(cudaMalloc(&h->d_alive, sizeof(int) * std::max(n, 1)));
-    CK(cudaMalloc(&h->d_status, sizeof(int) * std::max(n, 1)));
+    {
+        const size_t nn = (size_t)std::max(n, 1);
+        CK(ensure(h->b_results, nn * (sizeof(double) + 3 * sizeof(int))));
+        h->d_fitness = (double*)h->b_results.p;
+        h->d_ticks = (int*)(h->d_fitness + nn);
+        h->d_alive = h->d_ticks + nn;
+        h->d_status = h->d_alive + nn;
+    }
     h->h_fitness.assign(n, 0.0); h->h_ticks.assign(n, 0); h->h_alive.assign(n, 0); h->h_status.assign(n, 0);
     h->have_pop = true;
     return do_reset ? launch_reset(h) : REM2D_OK;
