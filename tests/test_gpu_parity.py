@@ -34,7 +34,8 @@ def assert_same_state(sg, so, what):
             what, k, (~same).sum(), same.size, np.abs(sg[k].astype(np.float64) - so[k]).max())
 
 
-@pytest.mark.parametrize("enc,flat,n,seed", [("direct", True, 256, 1), ("lsystem", False, 192, 2), ("ce", False, 128, 3)])
+@pytest.mark.parametrize("enc,flat,n,seed", [("direct", True, 256, 1), ("lsystem", False, 192, 2), ("ce", False, 128, 3),
+                                             ("cppn", False, 96, 4)])
 def test_first_100_ticks_bit_exact(enc, flat, n, seed):
     random.seed(seed)
     pop = flatten_population([Individual.random(encoding=enc) for _ in range(n)])
@@ -143,3 +144,22 @@ def test_park_cap_and_thresholds_do_not_change_results(monkeypatch):
         fg, tg = g.evaluate(pop, 400)
         assert np.array_equal(tg, to) and np.array_equal(fg, fo), park
         assert g.counters() == o.counters(), park
+
+
+def test_config2_direct_flat_1024_and_config4_mixed_cppn_ce():
+    """BASELINE.json configs 2 and 4 at test size: 1024 direct-encoding creatures on flat terrain, and a mixed CPPN / CE
+    population on rough terrain — per-creature fitness and lifetime identical to the oracle."""
+    from gym_rem2d_b200.population import random_population
+    pop2 = random_population(1024, ("direct",), seed=1, workers=4)
+    xs, ys = terrain.flat_terrain()
+    g, o = engines(ys)
+    fg, tg = g.evaluate(pop2, K.EVALUATION_STEPS)
+    fo, to = o.evaluate(pop2, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo)
+    pop4 = random_population(768, ("cppn", "ce"), seed=3, workers=4)
+    xs, ys = terrain.generate_terrain()
+    g, o = engines(ys)
+    fg, tg = g.evaluate(pop4, K.EVALUATION_STEPS)
+    fo, to = o.evaluate(pop4, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo)
+    assert g.counters() == o.counters()
