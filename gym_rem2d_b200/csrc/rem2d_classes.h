@@ -1,5 +1,5 @@
-// rem2d_classes.h — capacity classes and the per-class launch table (one translation unit per class, so the
-// template instantiations compile in parallel).
+// rem2d_classes.h — capacity classes and the launch interface of the four kernels (rem2d_kernels.cu; one translation
+// unit per kernel so that they compile in parallel). All classes run the SAME code: the class only selects a Layout.
 #pragma once
 #include <cuda_runtime.h>
 #include "rem2d_device.cuh"
@@ -19,20 +19,42 @@
     X(8, 44, 192, 10)
 #define N_CLASSES 9
 
-struct ClassOps {
-    int nb, nc, nt, nj, off_body, off_joint, off_cont, off_edge, words, hot_words;
-    cudaError_t (*set_attributes)();
-    void (*reset)(int grid, cudaStream_t st, float* state, const int* lane_creature, rem2d::DevPop p);
-    void (*step)(int grid, cudaStream_t st, float* state, int n_ticks, const rem2d::Terrain* ter, const rem2d::Consts* k,
-                 unsigned long long* counters);
-    void (*episode)(int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue, rem2d::DevPop p,
-                    const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks, int* alive,
-                    int* status, unsigned long long* counters, int park_ticks, int park_cap, float* park_state,
-                    int* park_creature, int* park_count);
-    void (*tail)(int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked, const rem2d::Terrain* ter,
-                 const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
-                 unsigned long long* counters);
+// When the bulk (lane-per-creature) episode kernel hands a creature over to the warp-per-creature tail kernel.
+struct ParkPolicy {
+    int ticks;        // park a creature that is still alive after this many ticks (0: never park)
+    int cap;          // at most this many creatures of the class are parked
+    int late_ticks;   // threshold for creatures pulled from position >= late_from of the class queue (the late starters
+    int late_from;    //   bound the makespan: they move to the low-latency kernel sooner)
+    int drain_lanes;  // once the queue is empty, a warp with <= this many live lanes parks them all and exits
+    // diagnostics (REM2D_TRACE=1): every 4th tick lane 0 of each warp records {globaltimer us, live lanes | tick << 8 |
+    // smid << 24}; REM2D_TRACE_SAMPLES entries per warp. Null in production.
+    unsigned int* trace;
 };
-#define X(i, NB, NC, NT) extern const ClassOps rem2d_class_ops_##i;
-REM2D_CLASSES(X)
-#undef X
+#define REM2D_TRACE_SAMPLES 1024
+
+// Launchers (rem2d_kernels.cu). `carve` = cudaFuncAttributePreferredSharedMemoryCarveout for all kernels.
+cudaError_t rem2d_set_kernel_attributes(int max_hot_words, int carve);
+void rem2d_launch_reset(const rem2d::Layout& L, int grid, cudaStream_t st, float* state, const int* lane_creature, rem2d::DevPop p);
+void rem2d_launch_step(const rem2d::Layout& L, int grid, cudaStream_t st, float* state, int n_ticks, const rem2d::Terrain* ter,
+                       const rem2d::Consts* k, unsigned long long* counters);
+void rem2d_launch_episode(const rem2d::Layout& L, int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue,
+                          rem2d::DevPop p, const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness,
+                          int* ticks, int* alive, int* status, unsigned long long* counters, ParkPolicy park, float* park_state,
+                          int* park_creature, int* park_count);
+void rem2d_launch_tail(const rem2d::Layout& L, int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot,
+                       int n_parked, const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks,
+                       int* alive, int* status, unsigned long long* counters);
+
+// Per-class view used by the host code.
+struct ClassOps {
+    rem2d::Layout L;
+    int nb, nc, nt, nj, off_body, off_joint, off_cont, off_edge, words, hot_words;
+    explicit ClassOps(int NB, int NC, int NT) : L(rem2d::make_layout(NB, NC, NT)) {
+        nb = L.nb; nc = L.nc; nt = L.nt; nj = L.nj; off_body = rem2d::S_COUNT; off_joint = L.off_joint; off_cont = L.off_cont;
+        off_edge = L.off_edge; words = L.words; hot_words = L.hot_words;
+    }
+    template <class... A> void reset(A... a) const { rem2d_launch_reset(L, a...); }
+    template <class... A> void step(A... a) const { rem2d_launch_step(L, a...); }
+    template <class... A> void episode(A... a) const { rem2d_launch_episode(L, a...); }
+    template <class... A> void tail(A... a) const { rem2d_launch_tail(L, a...); }
+};

@@ -19,12 +19,12 @@
 using namespace rem2d;
 
 // ------------------------------------------------------------------ capacity classes (rem2d_classes.h)
-static const ClassOps* const g_classes_p[N_CLASSES] = {
-#define X(i, NB, NC, NT) &rem2d_class_ops_##i,
+static const ClassOps g_classes_tab[N_CLASSES] = {
+#define X(i, NB, NC, NT) ClassOps(NB, NC, NT),
     REM2D_CLASSES(X)
 #undef X
 };
-#define g_classes(k) (*g_classes_p[k])
+#define g_classes(k) (g_classes_tab[k])
 
 // fitness / ticks / alive / status of every creature of a class -> creature-indexed outputs
 __global__ void gather_kernel(const float* state, const int* __restrict__ lane_creature, int n_lanes, int words,
@@ -115,7 +115,7 @@ struct ClassState {
     float* d_state = nullptr;
     int* d_lane_creature = nullptr;
     int* d_queue = nullptr;
-    Buf b_state, b_state2, b_lc, b_lcw0, b_lcw1, b_dst, b_small;   // backing storage (grow-only)
+    Buf b_state, b_state2, b_lc, b_lcw0, b_lcw1, b_dst, b_small, b_trace;   // backing storage (grow-only)
     // phased evaluation with survivor compaction (ping-pong buffers)
     float* d_state2 = nullptr;
     int* d_lc_work[2] = {nullptr, nullptr};   // lane -> creature maps of the compacted phases (d_lane_creature stays the static map)
@@ -139,7 +139,11 @@ struct rem2d_handle {
     Terrain* d_ter = nullptr;
     Consts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;
-    cudaStream_t tail_pool[16] = {};     // tail kernels are launched on demand, round robin over this pool
+    // Tail kernels are launched on demand, each on a stream of this pool that is idle at that moment: a tail kernel lives as
+    // long as its longest creature (hundreds of ms), so a second kernel queued behind it on the same stream would wait for
+    // it (and block its hardware queue for other streams). The pool grows when no stream is idle.
+    std::vector<cudaStream_t> tail_pool;
+    std::vector<char> tail_used;         // streams that received work during the current rem2d_run_episodes
     cudaStream_t poll_stream = nullptr;
     cudaEvent_t pool_done = nullptr;
     int* h_poll = nullptr;               // pinned [N_CLASSES]
@@ -184,7 +188,7 @@ static void free_population(rem2d_handle* h) {          // logical reset; the bu
 static void release_buffers(rem2d_handle* h) {
     for (auto& b : h->d_pop_mem) { if (b.p) cudaFree(b.p); b = Buf(); }
     for (auto& c : h->cls) {
-        Buf* bufs[] = {&c.b_state, &c.b_state2, &c.b_lc, &c.b_lcw0, &c.b_lcw1, &c.b_dst, &c.b_small};
+        Buf* bufs[] = {&c.b_state, &c.b_state2, &c.b_lc, &c.b_lcw0, &c.b_lcw1, &c.b_dst, &c.b_small, &c.b_trace};
         for (Buf* b : bufs) { if (b->p) cudaFree(b->p); *b = Buf(); }
         if (c.h_n_alive) cudaFreeHost(c.h_n_alive);
         c.h_n_alive = nullptr;
@@ -251,14 +255,19 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
         cudaEventCreate(&c.t_begin); cudaEventCreate(&c.t_end);
     }
     cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
+    h->tail_pool.resize(64);
     for (auto& st : h->tail_pool) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->pool_done, cudaEventDisableTiming);
     cudaMallocHost(&h->h_poll, sizeof(int) * 16);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device);
-    for (int q = 0; q < N_CLASSES; ++q)
-        if ((e = g_classes(q).set_attributes()) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
+    {
+        int carve = cudaSharedmemCarveoutMaxShared, max_hot = 0;
+        if (const char* ev = getenv("REM2D_CARVEOUT")) carve = atoi(ev);      // experiment: percent of the unified L1/shared array
+        for (int q = 0; q < N_CLASSES; ++q) max_hot = std::max(max_hot, g_classes(q).hot_words);
+        if ((e = rem2d_set_kernel_attributes(max_hot, carve)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
+    }
     *out = h;
     return REM2D_OK;
 }
@@ -362,11 +371,13 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
     h->creature_class.assign(n, -1);
     h->creature_lane.assign(n, -1);
     std::vector<std::vector<int>> members(N_CLASSES);
+    int min_class = 0;
+    if (const char* e = getenv("REM2D_MIN_CLASS")) min_class = std::max(0, std::min(N_CLASSES - 1, atoi(e)));   // experiment
     for (int c = 0; c < n; ++c) {
         int nb = pop->body_off[c + 1] - pop->body_off[c];
         if (nb < 1) { h->err = "upload: creature without a root body"; return REM2D_E_INVALID; }
         int k = -1;
-        for (int q = 0; q < N_CLASSES; ++q) if (nb <= g_classes(q).nb) { k = q; break; }
+        for (int q = min_class; q < N_CLASSES; ++q) if (nb <= g_classes(q).nb) { k = q; break; }
         if (k < 0) { char buf[128]; snprintf(buf, sizeof(buf), "upload: creature %d has %d bodies (> %d supported)", c, nb, g_classes(N_CLASSES - 1).nb); h->err = buf; return REM2D_E_CAPACITY; }
         int j0 = pop->body_off[c] - c;
         for (int j = 0; j < nb - 1; ++j)
@@ -426,7 +437,9 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         // (227 KB each) is divided among them in proportion to their work (bodies to simulate); a class never gets more
         // warps than it has batches, and what it cannot use is handed to the others. Without this the largest class
         // would occupy every SM until its last creature dies and the remaining classes would run after it.
-        double budget = (double)h->n_sms * 227.0 * 1024.0 * 0.98;
+        double smem_kb = 227.0;
+        if (const char* e = getenv("REM2D_SMEM_BUDGET_KB")) smem_kb = atof(e);       // experiments with a smaller carve-out
+        double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98;
         double work[N_CLASSES], smem[N_CLASSES];
         bool fixed[N_CLASSES];
         for (int k = 0; k < N_CLASSES; ++k) {
@@ -545,7 +558,7 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
             CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
             g_classes(k).episode(batches, h->user_stream, d_slots, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter, h->d_consts,
-                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, 0, 0, nullptr, nullptr, nullptr);
+                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, ParkPolicy{0, 0, 0, 0, 0}, nullptr, nullptr, nullptr);
             h->launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->user_stream));
@@ -640,8 +653,16 @@ static int launch_phased(rem2d_handle* h, int max_ticks) {
 static int launch_episodes(rem2d_handle* h, int max_ticks) {
     if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
     // creatures still alive after park_ticks are finished by the tail kernel (REM2D_PARK_TICKS=0 disables parking)
-    int park_ticks = 192;
-    if (const char* e = getenv("REM2D_PARK_TICKS")) park_ticks = atoi(e);
+    // Measured on B200 (tools/sweep_policy.py, 65536 L-system creatures): parking at 256 ticks (~0.5 % of the creatures) is
+    // the best trade: earlier thresholds park thousands of creatures whose tail kernels slow the bulk kernels down, later
+    // ones leave the longest-lived creatures on the slow lane-per-creature path; drain/late parking never paid off.
+    int park_ticks = 256, park_late = 256, drain_lanes = 0;
+    double late_frac = 1.0, cap_frac = 1.0;
+    if (const char* e = getenv("REM2D_PARK_TICKS")) park_ticks = park_late = atoi(e);
+    if (const char* e = getenv("REM2D_PARK_LATE")) park_late = atoi(e);
+    if (const char* e = getenv("REM2D_PARK_LATE_FROM")) late_frac = atof(e);
+    if (const char* e = getenv("REM2D_PARK_CAP")) cap_frac = atof(e);
+    if (const char* e = getenv("REM2D_DRAIN_LANES")) drain_lanes = atoi(e);
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
     CK(cudaEventRecord(h->ev_start, h->user_stream));
     int rc = fork_streams(h);
@@ -653,10 +674,20 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         CK(cudaEventRecord(cs.t_begin, cs.stream));
         CK(cudaMemsetAsync(cs.d_n_alive, 0, sizeof(int), cs.stream));
         CK(cudaMemsetAsync(cs.d_lc_work[0], 0, cs.lane_creature.size() * sizeof(int), cs.stream));     // "unpublished" markers
+        ParkPolicy park;
+        park.ticks = park_ticks < max_ticks ? park_ticks : 0;
+        park.cap = std::min(cs.n_members, std::max(32, std::min((int)(h->n_sms * 64 * cap_frac), (int)(cs.n_members * cap_frac))));
+        park.late_ticks = park_late; park.late_from = (int)(late_frac * cs.n_members); park.drain_lanes = drain_lanes;
+        park.trace = nullptr;
+        if (getenv("REM2D_TRACE")) {
+            const size_t bytes = (size_t)cs.episode_grid * REM2D_TRACE_SAMPLES * 2 * sizeof(unsigned int);
+            CK(ensure(cs.b_trace, bytes));
+            CK(cudaMemsetAsync(cs.b_trace.p, 0, bytes, cs.stream));
+            park.trace = (unsigned int*)cs.b_trace.p;
+        }
         g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
                              h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                             park_ticks < max_ticks ? park_ticks : 0, std::max(32, std::min(h->n_sms * 4, cs.n_members / 16)),
-                             cs.d_state2, cs.d_lc_work[0], cs.d_n_alive);
+                             park, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive);
         CK(cudaMemcpyAsync(cs.h_n_alive, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, cs.stream));
         CK(cudaEventRecord(cs.t_end, cs.stream));
         h->launches++;
@@ -669,7 +700,24 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         // kernel has finished.
         bool running[N_CLASSES];
         int launched[N_CLASSES];
-        int n_running = 0, rr = 0;
+        int n_running = 0;
+        size_t rr = 0;
+        h->tail_used.assign(h->tail_pool.size(), 0);
+        auto idle_stream = [&]() -> cudaStream_t {
+            for (size_t i = 0; i < h->tail_pool.size(); ++i) {
+                const size_t s = (rr + i) % h->tail_pool.size();
+                if (!h->tail_used[s] || cudaStreamQuery(h->tail_pool[s]) == cudaSuccess) { rr = s + 1; h->tail_used[s] = 1; return h->tail_pool[s]; }
+            }
+            cudaStream_t st = nullptr;
+            if (h->tail_pool.size() < 4096 && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess) {
+                h->tail_pool.push_back(st); h->tail_used.push_back(1);
+                return st;
+            }
+            cudaGetLastError();
+            const size_t s = rr++ % h->tail_pool.size();      // cannot grow: queue behind a busy stream
+            h->tail_used[s] = 1;
+            return h->tail_pool[s];
+        };
         for (int k = 0; k < N_CLASSES; ++k) { running[k] = h->cls[k].n_batches > 0; launched[k] = 0; n_running += running[k] ? 1 : 0; }
         while (n_running > 0) {
             bool finished_now[N_CLASSES];
@@ -688,7 +736,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
                 const int cnt = h->h_poll[k];
                 // early launches in chunks (a handful of creatures or whatever is there when the class is done)
                 if (cnt > launched[k] && (finished_now[k] || cnt - launched[k] >= 4)) {
-                    g_classes(k).tail(cnt - launched[k], h->tail_pool[rr++ & 15], cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
+                    g_classes(k).tail(cnt - launched[k], idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
                                       h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
                     CK(cudaGetLastError());
                     h->launches++;
@@ -698,8 +746,9 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
             }
             if (n_running > 0) std::this_thread::sleep_for(std::chrono::microseconds(500));
         }
-        for (auto& ts : h->tail_pool) {
-            CK(cudaEventRecord(h->pool_done, ts));
+        for (size_t s = 0; s < h->tail_pool.size(); ++s) {
+            if (!h->tail_used[s]) continue;
+            CK(cudaEventRecord(h->pool_done, h->tail_pool[s]));
             CK(cudaStreamWaitEvent(h->user_stream, h->pool_done, 0));
         }
     }
@@ -868,6 +917,20 @@ int rem2d_debug_class_timeline(rem2d_handle* h, float* out) {
     return N_CLASSES;
 }
 
+// Diagnostics: the REM2D_TRACE=1 samples of class k of the last rem2d_run_episodes: [warps][REM2D_TRACE_SAMPLES][2] uint32.
+// Returns the number of warps (0: none), negative on error; copies at most max_words words.
+int rem2d_debug_trace(rem2d_handle* h, int k, unsigned int* out, int64_t max_words) {
+    if (!h || !out || k < 0 || k >= N_CLASSES) return REM2D_E_INVALID;
+    ClassState& cs = h->cls[k];
+    if (!cs.b_trace.p || !cs.n_batches) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    size_t words = (size_t)cs.episode_grid * REM2D_TRACE_SAMPLES * 2;
+    if ((int64_t)words > max_words) words = (size_t)max_words;
+    CK(cudaMemcpy(out, cs.b_trace.p, words * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    return cs.episode_grid;
+}
+
 float rem2d_last_step_ms(rem2d_handle* h) { return h ? h->last_ms : 0.0f; }
 int64_t rem2d_launch_count(rem2d_handle* h) { return h ? h->launches : 0; }
 
@@ -890,9 +953,9 @@ int rem2d_read_state(rem2d_handle* h, rem2d_state_view* out) {
             if (c < 0) continue;
             const float* g = st.data() + (gl >> 5) * (size_t)ci.words * 32 + (gl & 31);
             auto S = [&](int f) { return g[f * 32]; };
-            auto B = [&](int f, int i) { return g[(ci.off_body + f * ci.nb + i) * 32]; };
-            auto J = [&](int f, int j) { return g[(ci.off_joint + f * ci.nj + j) * 32]; };
-            auto C = [&](int f, int q) { return g[(ci.off_cont + f * ci.nc + q) * 32]; };
+            auto B = [&](int f, int i) { return g[(ci.off_body + i * BF_COUNT + f) * 32]; };
+            auto J = [&](int f, int j) { return g[(ci.off_joint + j * JF_COUNT + f) * 32]; };
+            auto C = [&](int f, int q) { return g[(ci.off_cont + q * CF_COUNT + f) * 32]; };
             int b0 = h->body_off[c], nb = h->body_off[c + 1] - b0, j0 = b0 - c;
             int awake = 0;
             for (int i = 0; i < nb; ++i) {

@@ -193,22 +193,34 @@ struct DevPop {
 // work counters kept in registers and flushed once per launch
 struct Cnt { unsigned int c[REM2D_N_COUNTERS]; };   // per lane per launch; summed into 64-bit totals
 
+// Capacities and section offsets of one capacity class. The layout is a RUN-TIME value (kernel parameter, i.e. constant
+// bank): all classes execute the SAME code image. With one template instantiation per class, warps of 7 different
+// 365 KB kernels shared each SM's instruction cache and every class ran 1.4-5x slower than alone (measured).
+// Within a section the words are element-major (element * FIELD_COUNT + field), so that field offsets are immediates.
+struct Layout {
+    int nb, nj, nc, nt;                        // bodies, joints, contact-pool slots, hot (shared memory) touching contacts
+    int off_joint, off_cont, off_edge, off_spill, words;      // cold block, words per lane (bodies start at S_COUNT)
+    int hoff_joint, hoff_cont, hot_words;                     // hot block, words per lane (bodies start at 0)
+};
+__host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
+    Layout L;
+    L.nb = NB; L.nj = NB - 1 > 0 ? NB - 1 : 1; L.nc = NC; L.nt = NT;
+    L.off_joint = S_COUNT + BF_COUNT * NB;
+    L.off_cont = L.off_joint + JF_COUNT * L.nj;
+    L.off_edge = L.off_cont + CF_COUNT * NC;                  // alpha0 of the static edge bodies
+    L.off_spill = L.off_edge + RB_MAX_EDGES;                  // touching contacts beyond NT spill to HBM
+    L.words = L.off_spill + HC_COUNT * (NC - NT);
+    L.hoff_joint = HB_COUNT * NB;
+    L.hoff_cont = L.hoff_joint + HJ_COUNT * L.nj;
+    L.hot_words = L.hoff_cont + HC_COUNT * NT;
+    return L;
+}
+
 // HS = lane stride of the hot (shared memory) block: 32 when a warp holds 32 creatures (bank == lane), 1 when a whole
 // warp works on one creature (tail kernel).
-template <int NB, int NC, int NT, int HS = 32>
+template <int HS = 32>
 struct Sim {
-    static constexpr int NJ = NB - 1 > 0 ? NB - 1 : 1;
-    static constexpr int OFF_BODY = S_COUNT;
-    static constexpr int OFF_JOINT = OFF_BODY + BF_COUNT * NB;
-    static constexpr int OFF_CONT = OFF_JOINT + JF_COUNT * NJ;
-    static constexpr int OFF_EDGE = OFF_CONT + CF_COUNT * NC;      // alpha0 of the static edge bodies
-    static constexpr int NS = NC - NT;                              // touching contacts beyond NT spill to HBM
-    static constexpr int OFF_SPILL = OFF_EDGE + RB_MAX_EDGES;
-    static constexpr int WORDS = OFF_SPILL + HC_COUNT * NS;
-    static constexpr int HOFF_JOINT = HB_COUNT * NB;
-    static constexpr int HOFF_CONT = HOFF_JOINT + HJ_COUNT * NJ;
-    static constexpr int HOT_WORDS = HOFF_CONT + HC_COUNT * NT;
-
+    Layout L;
     float* g;                 // cold block of this batch, already offset by lane
     float* h;                 // hot block of this warp in shared memory, already offset by lane
     const Terrain* __restrict__ ter;
@@ -222,33 +234,34 @@ struct Sim {
     __device__ __forceinline__ void setSi(int f, int v) { g[f * 32] = __int_as_float(v); }
     __device__ __forceinline__ double Sd(int f) { return __hiloint2double(Si(f + 1), Si(f)); }
     __device__ __forceinline__ void setSd(int f, double v) { setSi(f, __double2loint(v)); setSi(f + 1, __double2hiint(v)); }
-    __device__ __forceinline__ float& B(int f, int i) { return g[(OFF_BODY + f * NB + i) * 32]; }
+    __device__ __forceinline__ float& B(int f, int i) { return g[(S_COUNT + i * BF_COUNT + f) * 32]; }
     __device__ __forceinline__ int Bi(int f, int i) { return __float_as_int(B(f, i)); }
     __device__ __forceinline__ void setBi(int f, int i, int v) { B(f, i) = __int_as_float(v); }
-    __device__ __forceinline__ float& J(int f, int j) { return g[(OFF_JOINT + f * NJ + j) * 32]; }
+    __device__ __forceinline__ float& J(int f, int j) { return g[(L.off_joint + j * JF_COUNT + f) * 32]; }
     __device__ __forceinline__ int Ji(int f, int j) { return __float_as_int(J(f, j)); }
     __device__ __forceinline__ void setJi(int f, int j, int v) { J(f, j) = __int_as_float(v); }
     __device__ __forceinline__ double Jd(int f, int j) { return __hiloint2double(Ji(f + 1, j), Ji(f, j)); }
     __device__ __forceinline__ void setJd(int f, int j, double v) { setJi(f, j, __double2loint(v)); setJi(f + 1, j, __double2hiint(v)); }
-    __device__ __forceinline__ float& C(int f, int c) { return g[(OFF_CONT + f * NC + c) * 32]; }
+    __device__ __forceinline__ float& C(int f, int c) { return g[(L.off_cont + c * CF_COUNT + f) * 32]; }
     __device__ __forceinline__ int Ci(int f, int c) { return __float_as_int(C(f, c)); }
     __device__ __forceinline__ void setCi(int f, int c, int v) { C(f, c) = __int_as_float(v); }
-    __device__ __forceinline__ float& EA(int e) { return g[(OFF_EDGE + e) * 32]; }
-    __device__ __forceinline__ float& HB(int f, int i) { return h[(f * NB + i) * HS]; }
-    __device__ __forceinline__ float& HJ(int f, int j) { return h[(HOFF_JOINT + f * NJ + j) * HS]; }
+    __device__ __forceinline__ float& EA(int e) { return g[(L.off_edge + e) * 32]; }
+    __device__ __forceinline__ float& HB(int f, int i) { return h[(i * HB_COUNT + f) * HS]; }
+    __device__ __forceinline__ float& HJ(int f, int j) { return h[(L.hoff_joint + j * HJ_COUNT + f) * HS]; }
     __device__ __forceinline__ int HJi(int f, int j) { return __float_as_int(HJ(f, j)); }
-    // Hot contact slot t: shared memory for t < NT, a spill region of the cold block otherwise. The two
-    // call sites of for_contacts() are specialised by the compiler (LDS/STS vs LDG/STG).
+    // Hot contact slot t: shared memory for t < NT, a spill region of the cold block otherwise. The callee gets the
+    // address of field 0 and the stride between fields; the two call sites are specialised by the compiler
+    // (LDS/STS vs LDG/STG).
     template <class F>
     __device__ __forceinline__ void for_contacts(int nt, F f) {
-        const int n1 = nt < NT ? nt : NT;
-        for (int t = 0; t < n1; ++t) f(h + (HOFF_CONT + t) * HS, NT * HS, t);
-        for (int t = NT; t < nt; ++t) f(g + (OFF_SPILL + (t - NT)) * 32, NS * 32, t);
+        const int n1 = nt < L.nt ? nt : L.nt;
+        for (int t = 0; t < n1; ++t) f(h + (L.hoff_cont + t * HC_COUNT) * HS, HS, t);
+        for (int t = L.nt; t < nt; ++t) f(g + (L.off_spill + (t - L.nt) * HC_COUNT) * 32, 32, t);
     }
     template <class F>
     __device__ __forceinline__ void with_contact(int t, F f) {
-        if (t < NT) f(h + (HOFF_CONT + t) * HS, NT * HS);
-        else f(g + (OFF_SPILL + (t - NT)) * 32, NS * 32);
+        if (t < L.nt) f(h + (L.hoff_cont + t * HC_COUNT) * HS, HS);
+        else f(g + (L.off_spill + (t - L.nt) * HC_COUNT) * 32, 32);
     }
 
     __device__ __forceinline__ int key_body(int key) { return key & 0xff; }
@@ -426,7 +439,7 @@ struct Sim {
                 if (!(Bi(BF_FLAGS, b) & BFL_MOVED)) continue;
                 if (!overlap_edge(e, b)) continue;
                 if (find_contact(nc, b, e) >= 0) continue;
-                if (nc == NC) { setSi(S_STATUS, Si(S_STATUS) | ST_POOL_OVERFLOW); continue; }
+                if (nc == L.nc) { setSi(S_STATUS, Si(S_STATUS) | ST_POOL_OVERFLOW); continue; }
                 setCi(CF_KEY, nc, b | (e << 8) | (CK_ENABLED << 16));
                 C(CF_TOI, nc) = 1.0f;
                 C(CF_P0N, nc) = 0.0f; C(CF_P0T, nc) = 0.0f; C(CF_P1N, nc) = 0.0f; C(CF_P1T, nc) = 0.0f;
@@ -1557,7 +1570,7 @@ struct Sim {
     // soon as each of its bodies has version it * degree(body) + rank(constraint within the body's sequence). Every
     // solve therefore reads exactly the velocities it would read in the sequential order — results are bit-identical —
     // while independent constraints, also of consecutive iterations, run concurrently in different lanes.
-    // `ver` is NB ints of shared memory. Must be called by all 32 lanes.
+    // `ver` is nb ints of shared memory. Must be called by all 32 lanes.
     __device__ void wavefront_velocity(int nt, int* ver, int lane) {
         const int n = nj + nt;
         const int vit = k->vel_iters;

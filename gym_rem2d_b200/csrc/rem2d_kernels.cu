@@ -1,0 +1,244 @@
+// rem2d_kernels.cu — the four kernels of the hot path. Compiled once per kernel (-DREM2D_KERNEL_ID=0..3) so the
+// translation units build in parallel; every capacity class runs the same code with its own Layout (kernel parameter).
+#include <cstdlib>
+#include "rem2d_classes.h"
+
+using namespace rem2d;
+
+#if REM2D_KERNEL_ID == 0
+// Build the world of every creature of a class (static creature -> lane mapping, used by rem2d_step).
+__global__ void __launch_bounds__(32) reset_kernel(const __grid_constant__ Layout L, float* state, const int* __restrict__ lane_creature,
+                                                   DevPop p) {
+    const int lane = threadIdx.x, batch = blockIdx.x;
+    Sim<32> sim;
+    sim.L = L;
+    sim.g = state + (size_t)batch * L.words * 32 + lane;
+    sim.build_world(p, lane_creature[batch * 32 + lane]);
+}
+void rem2d_launch_reset(const Layout& L, int grid, cudaStream_t st, float* state, const int* lane_creature, DevPop p) {
+    reset_kernel<<<grid, 32, 0, st>>>(L, state, lane_creature, p);
+}
+#endif
+
+#if REM2D_KERNEL_ID == 1
+// One warp per batch of 32 creatures; each lane advances its creature by up to n_ticks ticks.
+__global__ void __launch_bounds__(32, 1) step_kernel(const __grid_constant__ Layout L, float* state, int n_ticks,
+                                                     const Terrain* __restrict__ ter, const Consts* __restrict__ k,
+                                                     unsigned long long* counters) {
+    extern __shared__ float hot[];
+    const int lane = threadIdx.x, batch = blockIdx.x;
+    Sim<32> sim;
+    sim.L = L;
+    sim.g = state + (size_t)batch * L.words * 32 + lane;
+    sim.h = hot + lane;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
+    if (sim.nb > 0) {
+        for (int t = 0; t < n_ticks; ++t) {
+            if (!sim.Si(S_ALIVE)) break;
+            sim.tick();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
+        unsigned long long v = sim.cnt.c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&counters[i], v);
+    }
+}
+void rem2d_launch_step(const Layout& L, int grid, cudaStream_t st, float* state, int n_ticks, const Terrain* ter, const Consts* k,
+                       unsigned long long* counters) {
+    step_kernel<<<grid, 32, L.hot_words * 128, st>>>(L, state, n_ticks, ter, k, counters);
+}
+#endif
+
+#if REM2D_KERNEL_ID == 2
+// Whole episodes with dynamic lane refill: every lane pulls the next creature of its class from a queue
+// (big creatures first), builds its world in the lane's column of the warp's state block, ticks it until the
+// episode ends, writes fitness / ticks and pulls the next one. Lanes of a warp are therefore always busy until
+// the queue drains, instead of idling until the longest-lived creature of a fixed batch dies; and the cold
+// state of the few hundred resident warps stays L2-resident.
+__global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ Layout L, float* slots, const int* __restrict__ order,
+                                                        int n_order, int* queue, DevPop p, const Terrain* __restrict__ ter,
+                                                        const Consts* __restrict__ k, int max_ticks, double* fitness, int* ticks,
+                                                        int* alive, int* status, unsigned long long* counters, ParkPolicy park,
+                                                        float* park_state, int* park_creature, int* park_count) {
+    extern __shared__ float hot[];
+    const int lane = threadIdx.x;
+    Sim<32> sim;
+    sim.L = L;
+    sim.g = slots + (size_t)blockIdx.x * L.words * 32 + lane;
+    sim.h = hot + lane;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    int my = -1, park_at = park.ticks, loop_iter = 0;
+    bool exhausted = false;
+    Cnt snapshot = sim.cnt;
+    for (;;) {
+        if (my < 0 && !exhausted) {
+            int idx = atomicAdd(queue, 1);
+            if (idx < n_order) {
+                my = order[idx]; sim.build_world(p, my); snapshot = sim.cnt;
+                park_at = idx >= park.late_from ? park.late_ticks : park.ticks;
+            } else exhausted = true;
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, my >= 0);
+        if (park.trace && lane == 0 && (loop_iter & 3) == 0 && (loop_iter >> 2) < REM2D_TRACE_SAMPLES) {
+            unsigned long long t; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned int* tr = park.trace + ((size_t)blockIdx.x * REM2D_TRACE_SAMPLES + (loop_iter >> 2)) * 2;
+            tr[0] = (unsigned)(t / 1000ull);
+            tr[1] = (unsigned)__popc(live) | ((unsigned)(loop_iter & 0xffff) << 8) | (smid << 24);
+        }
+        ++loop_iter;
+        if (!live) break;
+        // drain: no refill any more and only a few lanes of this warp still work -> hand them to the tail kernel
+        const bool drain = park.drain_lanes > 0 && __popc(live) <= park.drain_lanes && __any_sync(0xffffffffu, exhausted);
+        if (my >= 0) {
+            sim.tick();
+            const int t = sim.Si(S_TICKS), st = sim.Si(S_STATUS);
+            if (!sim.Si(S_ALIVE) || t >= max_ticks || st) {
+                fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = st;
+                // a creature that outgrew a capacity of this class is re-run by the host in the next class up:
+                // its partial work must not be counted
+                if (st) sim.cnt = snapshot;
+                my = -1;
+            } else if (park.ticks > 0 && (t >= park_at || drain) && *(volatile int*)park_count < park.cap) {
+                // long-lived creature: park its state; the latency-oriented tail kernel (one warp per creature) finishes it.
+                // Only a bounded number of creatures is parked (the tail kernel trades throughput for latency): in an evolved
+                // population where most creatures live long, the rest simply continue here.
+                // (the counter never exceeds the cap: the host hands every counted slot to a tail kernel)
+                int slot = -1, seen = *(volatile int*)park_count;
+                while (seen < park.cap) {
+                    const int prev = atomicCAS(park_count, seen, seen + 1);
+                    if (prev == seen) { slot = seen; break; }
+                    seen = prev;
+                }
+                if (slot < 0) continue;
+                float* dst = park_state + (size_t)(slot >> 5) * L.words * 32 + (slot & 31);
+                for (int w = 0; w < L.words; ++w) dst[w * 32] = sim.g[w * 32];
+                __threadfence();                                 // the column is visible before the slot is published
+                atomicExch(&park_creature[slot], my + 1);        // 0 = allocated but not yet published
+                my = -1;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
+        unsigned long long v = sim.cnt.c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&counters[i], v);
+    }
+}
+void rem2d_launch_episode(const Layout& L, int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue, DevPop p,
+                          const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
+                          unsigned long long* counters, ParkPolicy park, float* park_state, int* park_creature, int* park_count) {
+    episode_kernel<<<grid, 32, L.hot_words * 128, st>>>(L, slots, order, n_order, queue, p, ter, k, max_ticks, fitness, ticks, alive,
+                                                        status, counters, park, park_state, park_creature, park_count);
+}
+#endif
+
+#if REM2D_KERNEL_ID == 3
+// Tail kernel: ONE WARP PER CREATURE for the few long-lived creatures that bound the makespan. Lane 0 runs the scalar
+// parts of the tick on the creature's parked column; all 32 lanes share the 180 velocity iterations as a bit-identical
+// dependency wavefront (Sim::wavefront_velocity), which cuts the per-tick latency of a large creature several times.
+// Dynamic shared memory: hot_words floats + nb version counters.
+__global__ void __launch_bounds__(32, 1) tail_kernel(const __grid_constant__ Layout L, float* park_state, int* park_creature,
+                                                     int first_slot, int n_parked, const Terrain* __restrict__ ter,
+                                                     const Consts* __restrict__ k, int max_ticks, double* fitness, int* ticks,
+                                                     int* alive, int* status, unsigned long long* counters) {
+    extern __shared__ float hot[];
+    int* ver = (int*)(hot + L.hot_words);
+    const int lane = threadIdx.x, slot = first_slot + blockIdx.x;
+    if ((int)blockIdx.x >= n_parked) return;
+    // the slot was allocated by an episode kernel that may still be running: wait until its column has been published
+    int my = -1;
+    if (lane == 0) {
+        int v;
+        while ((v = atomicAdd(&park_creature[slot], 0)) == 0) __nanosleep(500);
+        my = v - 1;
+        __threadfence();
+    }
+    my = __shfl_sync(0xffffffffu, my, 0);
+    Sim<1> sim;
+    sim.L = L;
+    sim.g = park_state + (size_t)(slot >> 5) * L.words * 32 + (slot & 31);
+    sim.h = hot;
+    sim.ter = ter; sim.k = k;
+#pragma unroll
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
+    sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
+    for (;;) {
+        int nt = 0, solved = 0;
+        if (lane == 0) solved = sim.tick_pre(nt) ? 1 : 0;
+        solved = __shfl_sync(0xffffffffu, solved, 0);
+        nt = __shfl_sync(0xffffffffu, nt, 0);
+        __syncwarp();
+        if (solved) {
+            if (sim.nj + nt <= 64) sim.wavefront_velocity(nt, ver, lane);
+            else if (lane == 0) sim.solve_velocity(nt);
+        }
+        __syncwarp();
+        int done = 0;
+        if (lane == 0) {
+            sim.tick_post(solved != 0, nt);
+            const int t = sim.Si(S_TICKS), st = sim.Si(S_STATUS);
+            if (!sim.Si(S_ALIVE) || t >= max_ticks || st) {
+                fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = st;
+                done = 1;
+            }
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done) break;
+    }
+    if (lane == 0) {
+        const int st = sim.Si(S_STATUS);
+        if (!st)
+            for (int i = 0; i < REM2D_N_COUNTERS; ++i)
+                if (sim.cnt.c[i]) atomicAdd(&counters[i], (unsigned long long)sim.cnt.c[i]);
+    }
+}
+void rem2d_launch_tail(const Layout& L, int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked,
+                       const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
+                       unsigned long long* counters) {
+    tail_kernel<<<grid, 32, (L.hot_words + L.nb) * 4, st>>>(L, park_state, park_creature, first_slot, n_parked, ter, k, max_ticks, fitness,
+                                                            ticks, alive, status, counters);
+}
+#endif
+
+// Attributes: every translation unit sets those of its own kernel; rem2d_set_kernel_attributes (kernel 0's unit) calls all.
+// All kernels that can be resident together should agree on the shared-memory carve-out of the SM: a small-smem kernel
+// (tail) would otherwise pin its SMs in a large-L1 configuration and lock the big episode CTAs of other classes out
+// (measured: 1.4x slower whole run when a tail kernel was resident next to the episode kernels).
+cudaError_t rem2d_attr_step(int max_hot_words, int carve);
+cudaError_t rem2d_attr_episode(int max_hot_words, int carve);
+cudaError_t rem2d_attr_tail(int max_hot_words, int carve);
+#if REM2D_KERNEL_ID == 0
+cudaError_t rem2d_set_kernel_attributes(int max_hot_words, int carve) {
+    cudaError_t e = rem2d_attr_step(max_hot_words, carve);
+    if (e != cudaSuccess) return e;
+    e = rem2d_attr_episode(max_hot_words, carve);
+    if (e != cudaSuccess) return e;
+    return rem2d_attr_tail(max_hot_words, carve);
+}
+#elif REM2D_KERNEL_ID == 1
+cudaError_t rem2d_attr_step(int max_hot_words, int carve) {
+    cudaError_t e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_hot_words * 128);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+}
+#elif REM2D_KERNEL_ID == 2
+cudaError_t rem2d_attr_episode(int max_hot_words, int carve) {
+    cudaError_t e = cudaFuncSetAttribute(episode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_hot_words * 128);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(episode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+}
+#elif REM2D_KERNEL_ID == 3
+cudaError_t rem2d_attr_tail(int max_hot_words, int carve) {
+    return cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+}
+#endif
