@@ -29,6 +29,7 @@ struct ParkPolicy {
     // diagnostics (REM2D_TRACE=1): every 4th tick lane 0 of each warp records {globaltimer us, live lanes | tick << 8 |
     // smid << 24}; REM2D_TRACE_SAMPLES entries per warp. Null in production.
     unsigned int* trace;
+    unsigned int* tail_trace;   // per park slot: {us parked, us tail warp started, us finished, ticks run by the tail warp}
 };
 #define REM2D_TRACE_SAMPLES 1024
 
@@ -43,7 +44,7 @@ void rem2d_launch_episode(const rem2d::Layout& L, int grid, cudaStream_t st, flo
                           int* park_creature, int* park_count);
 void rem2d_launch_tail(const rem2d::Layout& L, int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot,
                        int n_parked, const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks,
-                       int* alive, int* status, unsigned long long* counters);
+                       int* alive, int* status, unsigned long long* counters, unsigned int* tail_trace);
 
 // Per-class view used by the host code.
 struct ClassOps {

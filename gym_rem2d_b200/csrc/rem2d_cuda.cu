@@ -115,7 +115,7 @@ struct ClassState {
     float* d_state = nullptr;
     int* d_lane_creature = nullptr;
     int* d_queue = nullptr;
-    Buf b_state, b_state2, b_lc, b_lcw0, b_lcw1, b_dst, b_small, b_trace;   // backing storage (grow-only)
+    Buf b_state, b_state2, b_lc, b_lcw0, b_lcw1, b_dst, b_small, b_trace, b_ttrace;   // backing storage (grow-only)
     // phased evaluation with survivor compaction (ping-pong buffers)
     float* d_state2 = nullptr;
     int* d_lc_work[2] = {nullptr, nullptr};   // lane -> creature maps of the compacted phases (d_lane_creature stays the static map)
@@ -188,7 +188,7 @@ static void free_population(rem2d_handle* h) {          // logical reset; the bu
 static void release_buffers(rem2d_handle* h) {
     for (auto& b : h->d_pop_mem) { if (b.p) cudaFree(b.p); b = Buf(); }
     for (auto& c : h->cls) {
-        Buf* bufs[] = {&c.b_state, &c.b_state2, &c.b_lc, &c.b_lcw0, &c.b_lcw1, &c.b_dst, &c.b_small, &c.b_trace};
+        Buf* bufs[] = {&c.b_state, &c.b_state2, &c.b_lc, &c.b_lcw0, &c.b_lcw1, &c.b_dst, &c.b_small, &c.b_trace, &c.b_ttrace};
         for (Buf* b : bufs) { if (b->p) cudaFree(b->p); *b = Buf(); }
         if (c.h_n_alive) cudaFreeHost(c.h_n_alive);
         c.h_n_alive = nullptr;
@@ -437,7 +437,8 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         // (227 KB each) is divided among them in proportion to their work (bodies to simulate); a class never gets more
         // warps than it has batches, and what it cannot use is handed to the others. Without this the largest class
         // would occupy every SM until its last creature dies and the remaining classes would run after it.
-        double smem_kb = 227.0;
+        double smem_kb = 227.0, small_weight = 1.0;
+        if (const char* e = getenv("REM2D_SMALL_WEIGHT")) small_weight = atof(e);    // experiment: share of the small classes
         if (const char* e = getenv("REM2D_SMEM_BUDGET_KB")) smem_kb = atof(e);       // experiments with a smaller carve-out
         double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98;
         double work[N_CLASSES], smem[N_CLASSES];
@@ -447,6 +448,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
             // per-creature cost ~ tick latency of its size: measured ~0.3 ms + 0.085 ms per body for a resident warp; lone
             // bodies fall asleep after landing and cost almost nothing
             for (int c : members[k]) { int nbc = pop->body_off[c + 1] - pop->body_off[c]; work[k] += nbc == 1 ? 1.0 : 3.5 + nbc; }
+            if (g_classes(k).nb <= 8) work[k] *= small_weight;
             h->cls[k].episode_grid = 0;
         }
         // warps_k = W * work_k with W such that sum_k warps_k * smem_k = budget: every class then needs about the same
@@ -558,7 +560,7 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
             CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
             g_classes(k).episode(batches, h->user_stream, d_slots, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter, h->d_consts,
-                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, ParkPolicy{0, 0, 0, 0, 0}, nullptr, nullptr, nullptr);
+                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, ParkPolicy{0, 0, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr);
             h->launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->user_stream));
@@ -678,8 +680,12 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         park.ticks = park_ticks < max_ticks ? park_ticks : 0;
         park.cap = std::min(cs.n_members, std::max(32, std::min((int)(h->n_sms * 64 * cap_frac), (int)(cs.n_members * cap_frac))));
         park.late_ticks = park_late; park.late_from = (int)(late_frac * cs.n_members); park.drain_lanes = drain_lanes;
-        park.trace = nullptr;
+        park.trace = nullptr; park.tail_trace = nullptr;
         if (getenv("REM2D_TRACE")) {
+            const size_t tb = (size_t)std::max(cs.n_members, 1) * 4 * sizeof(unsigned int);
+            CK(ensure(cs.b_ttrace, tb));
+            CK(cudaMemsetAsync(cs.b_ttrace.p, 0, tb, cs.stream));
+            park.tail_trace = (unsigned int*)cs.b_ttrace.p;
             const size_t bytes = (size_t)cs.episode_grid * REM2D_TRACE_SAMPLES * 2 * sizeof(unsigned int);
             CK(ensure(cs.b_trace, bytes));
             CK(cudaMemsetAsync(cs.b_trace.p, 0, bytes, cs.stream));
@@ -699,7 +705,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         // creatures overlap the bulk instead of extending the run; the last launch of a class happens when its episode
         // kernel has finished.
         bool running[N_CLASSES];
-        int launched[N_CLASSES];
+        int launched[N_CLASSES], waited[N_CLASSES] = {};
         int n_running = 0;
         size_t rr = 0;
         h->tail_used.assign(h->tail_pool.size(), 0);
@@ -735,9 +741,12 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
                 ClassState& cs = h->cls[k];
                 const int cnt = h->h_poll[k];
                 // early launches in chunks (a handful of creatures or whatever is there when the class is done)
-                if (cnt > launched[k] && (finished_now[k] || cnt - launched[k] >= 4)) {
+                if (cnt > launched[k]) ++waited[k]; else waited[k] = 0;
+                if (cnt > launched[k] && (finished_now[k] || cnt - launched[k] >= 4 || waited[k] >= 3)) {
+                    waited[k] = 0;
                     g_classes(k).tail(cnt - launched[k], idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
-                                      h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+                                      h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
+                                      getenv("REM2D_TRACE") ? (unsigned int*)cs.b_ttrace.p : nullptr);
                     CK(cudaGetLastError());
                     h->launches++;
                     launched[k] = cnt;
@@ -929,6 +938,21 @@ int rem2d_debug_trace(rem2d_handle* h, int k, unsigned int* out, int64_t max_wor
     if ((int64_t)words > max_words) words = (size_t)max_words;
     CK(cudaMemcpy(out, cs.b_trace.p, words * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     return cs.episode_grid;
+}
+
+// Diagnostics: per park slot {us parked, us tail start, us tail end, tail ticks} of class k (REM2D_TRACE=1). Returns #slots.
+int rem2d_debug_tail_trace(rem2d_handle* h, int k, unsigned int* out, int64_t max_words) {
+    if (!h || !out || k < 0 || k >= N_CLASSES) return REM2D_E_INVALID;
+    ClassState& cs = h->cls[k];
+    if (!cs.b_ttrace.p || !cs.n_batches) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    int parked = 0;
+    CK(cudaMemcpy(&parked, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost));
+    size_t words = (size_t)parked * 4;
+    if ((int64_t)words > max_words) words = (size_t)max_words;
+    CK(cudaMemcpy(out, cs.b_ttrace.p, words * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    return parked;
 }
 
 float rem2d_last_step_ms(rem2d_handle* h) { return h ? h->last_ms : 0.0f; }

@@ -217,10 +217,10 @@ __host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
 }
 
 // HS = lane stride of the hot (shared memory) block: 32 when a warp holds 32 creatures (bank == lane), 1 when a whole
-// warp works on one creature (tail kernel).
-template <int HS = 32>
+// warp works on one creature (tail mode). A run-time value so that both modes share one code image.
 struct Sim {
     Layout L;
+    int HS;
     float* g;                 // cold block of this batch, already offset by lane
     float* h;                 // hot block of this warp in shared memory, already offset by lane
     const Terrain* __restrict__ ter;

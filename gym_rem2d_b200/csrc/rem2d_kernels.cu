@@ -1,4 +1,4 @@
-// rem2d_kernels.cu — the four kernels of the hot path. Compiled once per kernel (-DREM2D_KERNEL_ID=0..3) so the
+// rem2d_kernels.cu — the three kernels of the hot path (reset, step, episode with its bulk and tail modes). Compiled once per kernel (-DREM2D_KERNEL_ID=0..3) so the
 // translation units build in parallel; every capacity class runs the same code with its own Layout (kernel parameter).
 #include <cstdlib>
 #include "rem2d_classes.h"
@@ -10,8 +10,8 @@ using namespace rem2d;
 __global__ void __launch_bounds__(32) reset_kernel(const __grid_constant__ Layout L, float* state, const int* __restrict__ lane_creature,
                                                    DevPop p) {
     const int lane = threadIdx.x, batch = blockIdx.x;
-    Sim<32> sim;
-    sim.L = L;
+    Sim sim;
+    sim.L = L; sim.HS = 32;
     sim.g = state + (size_t)batch * L.words * 32 + lane;
     sim.build_world(p, lane_creature[batch * 32 + lane]);
 }
@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(32, 1) step_kernel(const __grid_constant__ Lay
                                                      unsigned long long* counters) {
     extern __shared__ float hot[];
     const int lane = threadIdx.x, batch = blockIdx.x;
-    Sim<32> sim;
-    sim.L = L;
+    Sim sim;
+    sim.L = L; sim.HS = 32;
     sim.g = state + (size_t)batch * L.words * 32 + lane;
     sim.h = hot + lane;
     sim.ter = ter; sim.k = k;
@@ -55,27 +55,58 @@ void rem2d_launch_step(const Layout& L, int grid, cudaStream_t st, float* state,
 #endif
 
 #if REM2D_KERNEL_ID == 2
-// Whole episodes with dynamic lane refill: every lane pulls the next creature of its class from a queue
-// (big creatures first), builds its world in the lane's column of the warp's state block, ticks it until the
-// episode ends, writes fitness / ticks and pulls the next one. Lanes of a warp are therefore always busy until
-// the queue drains, instead of idling until the longest-lived creature of a fixed batch dies; and the cold
-// state of the few hundred resident warps stays L2-resident.
-__global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ Layout L, float* slots, const int* __restrict__ order,
-                                                        int n_order, int* queue, DevPop p, const Terrain* __restrict__ ter,
-                                                        const Consts* __restrict__ k, int max_ticks, double* fitness, int* ticks,
-                                                        int* alive, int* status, unsigned long long* counters, ParkPolicy park,
-                                                        float* park_state, int* park_creature, int* park_count) {
+// Whole episodes, two modes of ONE kernel (one code image: co-resident warps of both modes share the instruction cache).
+//
+// mode 0, bulk: one lane per creature with dynamic lane refill: every lane pulls the next creature of its class from a
+// queue (big creatures first), builds its world in the lane's column of the warp's state block, ticks it until the
+// episode ends, writes fitness / ticks and pulls the next one. Lanes of a warp are therefore always busy until the
+// queue drains, instead of idling until the longest-lived creature of a fixed batch dies; and the cold state of the
+// few hundred resident warps stays L2-resident. Long-lived creatures are parked for mode 1.
+//
+// mode 1, tail: ONE WARP PER CREATURE for the long-lived creatures that bound the makespan. Lane 0 runs the scalar
+// parts of the tick on the creature's parked column; all 32 lanes share the 180 velocity iterations as a bit-identical
+// dependency wavefront (Sim::wavefront_velocity), which cuts the per-tick latency of a large creature several times.
+// Dynamic shared memory: hot_words * 128 B (bulk) or hot_words floats + nb version counters (tail).
+__global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ Layout L, int mode, float* slots,
+                                                        const int* __restrict__ order, int n_order, int* queue, DevPop p,
+                                                        const Terrain* __restrict__ ter, const Consts* __restrict__ k, int max_ticks,
+                                                        double* fitness, int* ticks, int* alive, int* status,
+                                                        unsigned long long* counters, ParkPolicy park, float* park_state,
+                                                        int* park_creature, int* park_count, int first_slot) {
     extern __shared__ float hot[];
     const int lane = threadIdx.x;
-    Sim<32> sim;
-    sim.L = L;
-    sim.g = slots + (size_t)blockIdx.x * L.words * 32 + lane;
-    sim.h = hot + lane;
+    const bool tail = mode != 0;
+    Sim sim;
+    sim.L = L; sim.HS = tail ? 1 : 32;
     sim.ter = ter; sim.k = k;
 #pragma unroll
     for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
     int my = -1, park_at = park.ticks, loop_iter = 0;
+    const int tail_slot = first_slot + blockIdx.x;
     bool exhausted = false;
+    int* ver = (int*)(hot + L.hot_words);
+    if (tail) {
+        // the slot was allocated by a bulk warp that may still be running: wait until its column has been published
+        const int slot = first_slot + blockIdx.x;
+        if (lane == 0) {
+            int v;
+            while ((v = atomicAdd(&park_creature[slot], 0)) == 0) __nanosleep(500);
+            my = v - 1;
+            __threadfence();
+        }
+        my = __shfl_sync(0xffffffffu, my, 0);
+        if (park.tail_trace && lane == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            park.tail_trace[slot * 4 + 1] = (unsigned)(t / 1000ull);
+        }
+        sim.g = park_state + (size_t)(slot >> 5) * L.words * 32 + (slot & 31);
+        sim.h = hot;
+        sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
+        exhausted = true;
+    } else {
+        sim.g = slots + (size_t)blockIdx.x * L.words * 32 + lane;
+        sim.h = hot + lane;
+    }
     Cnt snapshot = sim.cnt;
     for (;;) {
         if (my < 0 && !exhausted) {
@@ -96,10 +127,23 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ 
         }
         ++loop_iter;
         if (!live) break;
-        // drain: no refill any more and only a few lanes of this warp still work -> hand them to the tail kernel
-        const bool drain = park.drain_lanes > 0 && __popc(live) <= park.drain_lanes && __any_sync(0xffffffffu, exhausted);
-        if (my >= 0) {
-            sim.tick();
+        // drain: no refill any more and only a few lanes of this warp still work -> hand them to the tail mode
+        const bool drain = !tail && park.drain_lanes > 0 && __popc(live) <= park.drain_lanes && __any_sync(0xffffffffu, exhausted);
+        const bool active = tail ? lane == 0 : my >= 0;
+        int nt = 0, solved = 0;
+        if (active) solved = sim.tick_pre(nt) ? 1 : 0;
+        bool wave = false;
+        if (tail) {
+            solved = __shfl_sync(0xffffffffu, solved, 0);
+            nt = __shfl_sync(0xffffffffu, nt, 0);
+            wave = solved && sim.nj + nt <= 64;
+            __syncwarp();
+        }
+        if (wave) sim.wavefront_velocity(nt, ver, lane);
+        else if (active && solved) sim.solve_velocity(nt);
+        if (tail) __syncwarp();
+        if (active) {
+            sim.tick_post(solved != 0, nt);
             const int t = sim.Si(S_TICKS), st = sim.Si(S_STATUS);
             if (!sim.Si(S_ALIVE) || t >= max_ticks || st) {
                 fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = st;
@@ -107,25 +151,34 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ 
                 // its partial work must not be counted
                 if (st) sim.cnt = snapshot;
                 my = -1;
-            } else if (park.ticks > 0 && (t >= park_at || drain) && *(volatile int*)park_count < park.cap) {
-                // long-lived creature: park its state; the latency-oriented tail kernel (one warp per creature) finishes it.
-                // Only a bounded number of creatures is parked (the tail kernel trades throughput for latency): in an evolved
-                // population where most creatures live long, the rest simply continue here.
-                // (the counter never exceeds the cap: the host hands every counted slot to a tail kernel)
+            } else if (!tail && park.ticks > 0 && (t >= park_at || drain) && *(volatile int*)park_count < park.cap) {
+                // long-lived creature: park its state; the latency-oriented tail mode (one warp per creature) finishes it.
+                // (the counter never exceeds the cap: the host hands every counted slot to a tail launch)
                 int slot = -1, seen = *(volatile int*)park_count;
                 while (seen < park.cap) {
                     const int prev = atomicCAS(park_count, seen, seen + 1);
                     if (prev == seen) { slot = seen; break; }
                     seen = prev;
                 }
-                if (slot < 0) continue;
-                float* dst = park_state + (size_t)(slot >> 5) * L.words * 32 + (slot & 31);
-                for (int w = 0; w < L.words; ++w) dst[w * 32] = sim.g[w * 32];
-                __threadfence();                                 // the column is visible before the slot is published
-                atomicExch(&park_creature[slot], my + 1);        // 0 = allocated but not yet published
-                my = -1;
+                if (slot >= 0) {
+                    float* dst = park_state + (size_t)(slot >> 5) * L.words * 32 + (slot & 31);
+                    for (int w = 0; w < L.words; ++w) dst[w * 32] = sim.g[w * 32];
+                    if (park.tail_trace) {
+                        unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+                        park.tail_trace[slot * 4] = (unsigned)(tt / 1000ull);
+                    }
+                    __threadfence();                                 // the column is visible before the slot is published
+                    atomicExch(&park_creature[slot], my + 1);        // 0 = allocated but not yet published
+                    my = -1;
+                }
             }
         }
+        if (tail) my = __shfl_sync(0xffffffffu, my, 0);
+    }
+    if (tail && park.tail_trace && lane == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        park.tail_trace[tail_slot * 4 + 2] = (unsigned)(t / 1000ull);
+        park.tail_trace[tail_slot * 4 + 3] = (unsigned)loop_iter - 1u;
     }
 #pragma unroll
     for (int i = 0; i < REM2D_N_COUNTERS; ++i) {
@@ -137,76 +190,17 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ 
 void rem2d_launch_episode(const Layout& L, int grid, cudaStream_t st, float* slots, const int* order, int n_order, int* queue, DevPop p,
                           const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
                           unsigned long long* counters, ParkPolicy park, float* park_state, int* park_creature, int* park_count) {
-    episode_kernel<<<grid, 32, L.hot_words * 128, st>>>(L, slots, order, n_order, queue, p, ter, k, max_ticks, fitness, ticks, alive,
-                                                        status, counters, park, park_state, park_creature, park_count);
-}
-#endif
-
-#if REM2D_KERNEL_ID == 3
-// Tail kernel: ONE WARP PER CREATURE for the few long-lived creatures that bound the makespan. Lane 0 runs the scalar
-// parts of the tick on the creature's parked column; all 32 lanes share the 180 velocity iterations as a bit-identical
-// dependency wavefront (Sim::wavefront_velocity), which cuts the per-tick latency of a large creature several times.
-// Dynamic shared memory: hot_words floats + nb version counters.
-__global__ void __launch_bounds__(32, 1) tail_kernel(const __grid_constant__ Layout L, float* park_state, int* park_creature,
-                                                     int first_slot, int n_parked, const Terrain* __restrict__ ter,
-                                                     const Consts* __restrict__ k, int max_ticks, double* fitness, int* ticks,
-                                                     int* alive, int* status, unsigned long long* counters) {
-    extern __shared__ float hot[];
-    int* ver = (int*)(hot + L.hot_words);
-    const int lane = threadIdx.x, slot = first_slot + blockIdx.x;
-    if ((int)blockIdx.x >= n_parked) return;
-    // the slot was allocated by an episode kernel that may still be running: wait until its column has been published
-    int my = -1;
-    if (lane == 0) {
-        int v;
-        while ((v = atomicAdd(&park_creature[slot], 0)) == 0) __nanosleep(500);
-        my = v - 1;
-        __threadfence();
-    }
-    my = __shfl_sync(0xffffffffu, my, 0);
-    Sim<1> sim;
-    sim.L = L;
-    sim.g = park_state + (size_t)(slot >> 5) * L.words * 32 + (slot & 31);
-    sim.h = hot;
-    sim.ter = ter; sim.k = k;
-#pragma unroll
-    for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
-    sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
-    for (;;) {
-        int nt = 0, solved = 0;
-        if (lane == 0) solved = sim.tick_pre(nt) ? 1 : 0;
-        solved = __shfl_sync(0xffffffffu, solved, 0);
-        nt = __shfl_sync(0xffffffffu, nt, 0);
-        __syncwarp();
-        if (solved) {
-            if (sim.nj + nt <= 64) sim.wavefront_velocity(nt, ver, lane);
-            else if (lane == 0) sim.solve_velocity(nt);
-        }
-        __syncwarp();
-        int done = 0;
-        if (lane == 0) {
-            sim.tick_post(solved != 0, nt);
-            const int t = sim.Si(S_TICKS), st = sim.Si(S_STATUS);
-            if (!sim.Si(S_ALIVE) || t >= max_ticks || st) {
-                fitness[my] = sim.Sd(S_FIT_LO); ticks[my] = t; alive[my] = sim.Si(S_ALIVE); status[my] = st;
-                done = 1;
-            }
-        }
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done) break;
-    }
-    if (lane == 0) {
-        const int st = sim.Si(S_STATUS);
-        if (!st)
-            for (int i = 0; i < REM2D_N_COUNTERS; ++i)
-                if (sim.cnt.c[i]) atomicAdd(&counters[i], (unsigned long long)sim.cnt.c[i]);
-    }
+    episode_kernel<<<grid, 32, L.hot_words * 128, st>>>(L, 0, slots, order, n_order, queue, p, ter, k, max_ticks, fitness, ticks, alive,
+                                                        status, counters, park, park_state, park_creature, park_count, 0);
 }
 void rem2d_launch_tail(const Layout& L, int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked,
                        const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
-                       unsigned long long* counters) {
-    tail_kernel<<<grid, 32, (L.hot_words + L.nb) * 4, st>>>(L, park_state, park_creature, first_slot, n_parked, ter, k, max_ticks, fitness,
-                                                            ticks, alive, status, counters);
+                       unsigned long long* counters, unsigned int* tail_trace) {
+    (void)n_parked;      // grid == number of parked creatures handed over
+    ParkPolicy none = {0, 0, 0, 0, 0, nullptr, tail_trace};
+    episode_kernel<<<grid, 32, (L.hot_words + L.nb) * 4, st>>>(L, 1, nullptr, nullptr, 0, nullptr, DevPop(), ter, k, max_ticks, fitness,
+                                                               ticks, alive, status, counters, none, park_state, park_creature, nullptr,
+                                                               first_slot);
 }
 #endif
 
@@ -216,14 +210,11 @@ void rem2d_launch_tail(const Layout& L, int grid, cudaStream_t st, float* park_s
 // (measured: 1.4x slower whole run when a tail kernel was resident next to the episode kernels).
 cudaError_t rem2d_attr_step(int max_hot_words, int carve);
 cudaError_t rem2d_attr_episode(int max_hot_words, int carve);
-cudaError_t rem2d_attr_tail(int max_hot_words, int carve);
 #if REM2D_KERNEL_ID == 0
 cudaError_t rem2d_set_kernel_attributes(int max_hot_words, int carve) {
     cudaError_t e = rem2d_attr_step(max_hot_words, carve);
     if (e != cudaSuccess) return e;
-    e = rem2d_attr_episode(max_hot_words, carve);
-    if (e != cudaSuccess) return e;
-    return rem2d_attr_tail(max_hot_words, carve);
+    return rem2d_attr_episode(max_hot_words, carve);
 }
 #elif REM2D_KERNEL_ID == 1
 cudaError_t rem2d_attr_step(int max_hot_words, int carve) {
@@ -236,9 +227,5 @@ cudaError_t rem2d_attr_episode(int max_hot_words, int carve) {
     cudaError_t e = cudaFuncSetAttribute(episode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_hot_words * 128);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(episode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-}
-#elif REM2D_KERNEL_ID == 3
-cudaError_t rem2d_attr_tail(int max_hot_words, int carve) {
-    return cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
 }
 #endif
