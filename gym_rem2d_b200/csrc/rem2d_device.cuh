@@ -201,6 +201,7 @@ struct Layout {
     int nb, nj, nc, nt;                        // bodies, joints, contact-pool slots, hot (shared memory) touching contacts
     int off_joint, off_cont, off_edge, off_spill, words;      // cold block, words per lane (bodies start at S_COUNT)
     int hoff_joint, hoff_cont, hot_words;                     // hot block, words per lane (bodies start at 0)
+    int thoff_joint, thoff_cont, thot_rows;                   // hot block of the tail mode, rows of 32 words (see Sim)
 };
 __host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
     Layout L;
@@ -213,14 +214,21 @@ __host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
     L.hoff_joint = HB_COUNT * NB;
     L.hoff_cont = L.hoff_joint + HJ_COUNT * L.nj;
     L.hot_words = L.hoff_cont + HC_COUNT * NT;
+    L.thoff_joint = HB_COUNT * ((NB + 31) / 32);
+    L.thoff_cont = L.thoff_joint + HJ_COUNT * ((L.nj + 31) / 32);
+    L.thot_rows = L.thoff_cont + HC_COUNT * ((NT + 31) / 32);
     return L;
 }
 
-// HS = lane stride of the hot (shared memory) block: 32 when a warp holds 32 creatures (bank == lane), 1 when a whole
-// warp works on one creature (tail mode). A run-time value so that both modes share one code image.
+// Hot (shared memory) block: rows of 32 words, field f of an element at row (section + element_row * FIELD_COUNT + f).
+// Bulk mode (a warp holds 32 creatures): the column is the lane (already added to `h`), element_row = element index, so
+// bank == lane. Tail mode (a whole warp works on ONE creature): the column is the element index modulo 32 and
+// element_row = index / 32, so lanes that work on different elements hit different banks. Field offsets are immediates in
+// both modes and both modes share one code image (`tail` is a run-time flag).
 struct Sim {
     Layout L;
-    int HS;
+    bool tail;
+    int hj_off, hc_off;       // section rows of the joints / contacts for the current mode
     float* g;                 // cold block of this batch, already offset by lane
     float* h;                 // hot block of this warp in shared memory, already offset by lane
     const Terrain* __restrict__ ter;
@@ -246,8 +254,17 @@ struct Sim {
     __device__ __forceinline__ int Ci(int f, int c) { return __float_as_int(C(f, c)); }
     __device__ __forceinline__ void setCi(int f, int c, int v) { C(f, c) = __int_as_float(v); }
     __device__ __forceinline__ float& EA(int e) { return g[(L.off_edge + e) * 32]; }
-    __device__ __forceinline__ float& HB(int f, int i) { return h[(i * HB_COUNT + f) * HS]; }
-    __device__ __forceinline__ float& HJ(int f, int j) { return h[(L.hoff_joint + j * HJ_COUNT + f) * HS]; }
+    __device__ __forceinline__ void set_mode(bool tail_mode) {
+        tail = tail_mode;
+        hj_off = tail ? L.thoff_joint : L.hoff_joint;
+        hc_off = tail ? L.thoff_cont : L.hoff_cont;
+    }
+    __device__ __forceinline__ float* hot_elem(int section, int count, int e) {     // field 0 of element e
+        const int row = tail ? (e >> 5) : e, col = tail ? (e & 31) : 0;
+        return h + ((section + row * count) << 5) + col;
+    }
+    __device__ __forceinline__ float& HB(int f, int i) { return hot_elem(0, HB_COUNT, i)[f * 32]; }
+    __device__ __forceinline__ float& HJ(int f, int j) { return hot_elem(hj_off, HJ_COUNT, j)[f * 32]; }
     __device__ __forceinline__ int HJi(int f, int j) { return __float_as_int(HJ(f, j)); }
     // Hot contact slot t: shared memory for t < NT, a spill region of the cold block otherwise. The callee gets the
     // address of field 0 and the stride between fields; the two call sites are specialised by the compiler
@@ -255,12 +272,12 @@ struct Sim {
     template <class F>
     __device__ __forceinline__ void for_contacts(int nt, F f) {
         const int n1 = nt < L.nt ? nt : L.nt;
-        for (int t = 0; t < n1; ++t) f(h + (L.hoff_cont + t * HC_COUNT) * HS, HS, t);
+        for (int t = 0; t < n1; ++t) f(hot_elem(hc_off, HC_COUNT, t), 32, t);
         for (int t = L.nt; t < nt; ++t) f(g + (L.off_spill + (t - L.nt) * HC_COUNT) * 32, 32, t);
     }
     template <class F>
     __device__ __forceinline__ void with_contact(int t, F f) {
-        if (t < L.nt) f(h + (L.hoff_cont + t * HC_COUNT) * HS, HS);
+        if (t < L.nt) f(hot_elem(hc_off, HC_COUNT, t), 32);
         else f(g + (L.off_spill + (t - L.nt) * HC_COUNT) * 32, 32);
     }
 

@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(32) reset_kernel(const __grid_constant__ Layou
                                                    DevPop p) {
     const int lane = threadIdx.x, batch = blockIdx.x;
     Sim sim;
-    sim.L = L; sim.HS = 32;
+    sim.L = L; sim.set_mode(false);
     sim.g = state + (size_t)batch * L.words * 32 + lane;
     sim.build_world(p, lane_creature[batch * 32 + lane]);
 }
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(32, 1) step_kernel(const __grid_constant__ Lay
     extern __shared__ float hot[];
     const int lane = threadIdx.x, batch = blockIdx.x;
     Sim sim;
-    sim.L = L; sim.HS = 32;
+    sim.L = L; sim.set_mode(false);
     sim.g = state + (size_t)batch * L.words * 32 + lane;
     sim.h = hot + lane;
     sim.ter = ter; sim.k = k;
@@ -66,7 +66,7 @@ void rem2d_launch_step(const Layout& L, int grid, cudaStream_t st, float* state,
 // mode 1, tail: ONE WARP PER CREATURE for the long-lived creatures that bound the makespan. Lane 0 runs the scalar
 // parts of the tick on the creature's parked column; all 32 lanes share the 180 velocity iterations as a bit-identical
 // dependency wavefront (Sim::wavefront_velocity), which cuts the per-tick latency of a large creature several times.
-// Dynamic shared memory: hot_words * 128 B (bulk) or hot_words floats + nb version counters (tail).
+// Dynamic shared memory: hot_words * 128 B (bulk) or thot_rows * 128 B + nb version counters (tail).
 __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ Layout L, int mode, float* slots,
                                                         const int* __restrict__ order, int n_order, int* queue, DevPop p,
                                                         const Terrain* __restrict__ ter, const Consts* __restrict__ k, int max_ticks,
@@ -77,14 +77,14 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ 
     const int lane = threadIdx.x;
     const bool tail = mode != 0;
     Sim sim;
-    sim.L = L; sim.HS = tail ? 1 : 32;
+    sim.L = L; sim.set_mode(tail);
     sim.ter = ter; sim.k = k;
 #pragma unroll
     for (int i = 0; i < REM2D_N_COUNTERS; ++i) sim.cnt.c[i] = 0u;
     int my = -1, park_at = park.ticks, loop_iter = 0;
     const int tail_slot = first_slot + blockIdx.x;
     bool exhausted = false;
-    int* ver = (int*)(hot + L.hot_words);
+    int* ver = (int*)(hot + L.thot_rows * 32);       // tail mode only
     if (tail) {
         // the slot was allocated by a bulk warp that may still be running: wait until its column has been published
         const int slot = first_slot + blockIdx.x;
@@ -198,7 +198,7 @@ void rem2d_launch_tail(const Layout& L, int grid, cudaStream_t st, float* park_s
                        unsigned long long* counters, unsigned int* tail_trace) {
     (void)n_parked;      // grid == number of parked creatures handed over
     ParkPolicy none = {0, 0, 0, 0, 0, nullptr, tail_trace};
-    episode_kernel<<<grid, 32, (L.hot_words + L.nb) * 4, st>>>(L, 1, nullptr, nullptr, 0, nullptr, DevPop(), ter, k, max_ticks, fitness,
+    episode_kernel<<<grid, 32, (L.thot_rows * 32 + L.nb) * 4, st>>>(L, 1, nullptr, nullptr, 0, nullptr, DevPop(), ter, k, max_ticks, fitness,
                                                                ticks, alive, status, counters, none, park_state, park_creature, nullptr,
                                                                first_slot);
 }

@@ -1,3 +1,5 @@
-export SWEEP_ROUNDS=1
-export SWEEP_CFGS='[["default", null, {}], ["small 0.8", null, {"SMALL_WEIGHT": 0.8}], ["small 0.65", null, {"SMALL_WEIGHT": 0.65}], ["small 0.5", null, {"SMALL_WEIGHT": 0.5}], ["small 0.65 park 224", null, {"SMALL_WEIGHT": 0.65, "PARK_TICKS": 224}], ["small 0.65 park 224 drain 8 b213", null, {"SMALL_WEIGHT": 0.65, "PARK_TICKS": 224, "DRAIN_LANES": 8, "SMEM_BUDGET_KB": 213}], ["default", null, {}]]'
-timeout 600 python tools/sweep_policy.py 2>&1 | tail -9
+timeout 700 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+export SWEEP_ROUNDS=2
+export SWEEP_CFGS='[["default", null, {}], ["park 224", null, {"PARK_TICKS": 224}], ["park 192 b213", null, {"PARK_TICKS": 192, "SMEM_BUDGET_KB": 213}]]'
+timeout 600 python tools/sweep_policy.py 2>&1 | tail -8
+MIX=all timeout 120 python tools/trace_mix.py 2>&1 | tail -1
