@@ -240,7 +240,12 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         fp32_peak = eng.measure_fp32_peak()
         roofline = {"bound": "hbm", "achieved": abytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": abytes / (step_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                    "frac": abytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                    # profiles/r1_ncu_full_episode_kernel.txt: dram__bytes_read.sum + dram__bytes_write.sum of the dominant
+                    # launch (bulk mode, class NB=22 of this workload: 17075 creatures, 2.19 M creature-ticks, 3.8 GB algorithmic)
+                    "traffic": 2.659e9 if args.pop == 65536 and args.encoding == "lsystem" else None,
+                    "traffic_scope": "ncu DRAM read+write of the dominant launch only (bulk mode, class NB=22: 3.8e9 algorithmic "
+                                     "bytes by the same formula); achieved/peak/frac are for the whole step (all classes)",
                     "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                     "note": "the step is a chain of dependent fp32 ops on shared-memory state: neither HBM- nor tensor-bound; "
                             "see fp32_issue for the bounding resource"}

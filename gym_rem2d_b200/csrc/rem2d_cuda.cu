@@ -656,10 +656,13 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
     // creatures still alive after park_ticks are finished by the tail kernel (REM2D_PARK_TICKS=0 disables parking)
     // Measured on B200 (tools/sweep_policy.py, 65536 L-system creatures): parking at 256 ticks (~0.5 % of the creatures) is
-    // the best trade: earlier thresholds park thousands of creatures whose tail kernels slow the bulk kernels down, later
-    // ones leave the longest-lived creatures on the slow lane-per-creature path; drain/late parking never paid off.
+    // the best trade: a tail warp finishes a creature 3-4x sooner than its bulk lane would, but it occupies a whole warp, so
+    // earlier thresholds (thousands of parked creatures) slow the bulk down more than they shorten the critical path; later
+    // ones leave the longest-lived creatures on the slow path. Drain / late-start parking never paid off. The number of
+    // parked creatures per class is bounded (n/16, at most 4 per SM): in an evolved population where most creatures live
+    // long, the rest simply stay on their lanes.
     int park_ticks = 256, park_late = 256, drain_lanes = 0;
-    double late_frac = 1.0, cap_frac = 1.0;
+    double late_frac = 1.0, cap_frac = 1.0 / 16.0;
     if (const char* e = getenv("REM2D_PARK_TICKS")) park_ticks = park_late = atoi(e);
     if (const char* e = getenv("REM2D_PARK_LATE")) park_late = atoi(e);
     if (const char* e = getenv("REM2D_PARK_LATE_FROM")) late_frac = atof(e);

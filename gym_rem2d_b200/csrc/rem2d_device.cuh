@@ -110,14 +110,17 @@ __device__ __forceinline__ void sincos_kernel(double x, double& s, double& c) {
 }
 // b2Rot::Set: float kernel, same operation sequence as oracle sincos_kernel_f32 (Cody-Waite by pi/2 with short
 // constants + Cephes-style minimax polynomials); huge angles use the double kernel.
+// (the huge-angle path is a real call: rot_set is inlined at ~20 sites and the double kernel would be 10 % of the code)
+static __device__ __noinline__ Rot rot_set_huge(float a) {
+    Rot q;
+    double s, c;
+    sincos_kernel((double)a, s, c);
+    q.s = (float)s; q.c = (float)c;
+    return q;
+}
 __device__ __forceinline__ Rot rot_set(float a) {
     Rot q;
-    if (!(abs2(a) < 65536.0f)) {
-        double s, c;
-        sincos_kernel((double)a, s, c);
-        q.s = (float)s; q.c = (float)c;
-        return q;
-    }
+    if (!(abs2(a) < 65536.0f)) return rot_set_huge(a);
     float kf = floorf(a * 0.636619747f + 0.5f);
     float r = ((a - kf * 1.5703125f) - kf * 4.837512969970703125e-4f) - kf * 7.54978995489188216e-8f;
     float z = r * r;
@@ -229,6 +232,7 @@ struct Sim {
     Layout L;
     bool tail;
     int hj_off, hc_off;       // section rows of the joints / contacts for the current mode
+    int e_shift, e_mask;      // element -> (row, column): (e, 0) in bulk mode, (e >> 5, e & 31) in tail mode
     float* g;                 // cold block of this batch, already offset by lane
     float* h;                 // hot block of this warp in shared memory, already offset by lane
     const Terrain* __restrict__ ter;
@@ -258,10 +262,10 @@ struct Sim {
         tail = tail_mode;
         hj_off = tail ? L.thoff_joint : L.hoff_joint;
         hc_off = tail ? L.thoff_cont : L.hoff_cont;
+        e_shift = tail ? 5 : 0; e_mask = tail ? 31 : 0;
     }
     __device__ __forceinline__ float* hot_elem(int section, int count, int e) {     // field 0 of element e
-        const int row = tail ? (e >> 5) : e, col = tail ? (e & 31) : 0;
-        return h + ((section + row * count) << 5) + col;
+        return h + ((section + (e >> e_shift) * count) << 5) + (e & e_mask);
     }
     __device__ __forceinline__ float& HB(int f, int i) { return hot_elem(0, HB_COUNT, i)[f * 32]; }
     __device__ __forceinline__ float& HJ(int f, int j) { return hot_elem(hj_off, HJ_COUNT, j)[f * 32]; }

@@ -33,7 +33,7 @@ print('stall mix (% of samples):', {n[6:]:round(100*tot[n]/tot['# Samples'],1) f
 src=open(hdr).read().split('\n')
 def fn_of(line):
     for i in range(min(line,len(src)),0,-1):
-        m=re.match(r'\s*(template\s*<[^>]*>\s*)?__device__[\w\s]*?\b(\w+)\s*\(',src[i-1])
+        m=re.match(r'\s*(template\s*<[^>]*>\s*)?__device__[\w\s\*&]*?\b(\w+)\s*\(',src[i-1])
         if m: return m.group(2)
     return '?'
 fagg=collections.defaultdict(lambda:[0.0,0.0,0.0,0.0])
