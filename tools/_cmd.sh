@@ -1,7 +1,4 @@
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
-timeout 300 python bench.py --steps 3 --warmup 3 2>gpurun_out/bench_final.err | tee gpurun_out/bench_final.json | cut -c1-400
-timeout 600 ncu --metrics gpu__time_duration.sum,launch__grid_size,launch__shared_mem_per_block_dynamic --clock-control none -c 2000 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1; tail -c 300 gpurun_out/bench_under_ncu.log; wc -l gpurun_out/launches_final.csv
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:episode_kernel --launch-skip 7 --launch-count 1 -o /tmp/bulk python tools/profile_bulk.py > gpurun_out/ncu_bulk.log 2>&1; tail -3 gpurun_out/ncu_bulk.log
-ncu -i /tmp/bulk.ncu-rep --page raw --csv > gpurun_out/bulk_raw.csv 2>/dev/null
-ncu -i /tmp/bulk.ncu-rep --page source --csv > gpurun_out/bulk_src.csv 2>/dev/null
-ls -la gpurun_out/bulk_*.csv
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python bench.py 2>gpurun_out/bench_n1.err | tee gpurun_out/bench_r1_n1.json | cut -c1-200
+timeout 300 python bench.py --impl reference --steps 1 --warmup 1 2>/dev/null | tee gpurun_out/bench_r1_ref.json | cut -c1-200
