@@ -42,6 +42,9 @@ void rem2d_launch_episode(const rem2d::Layout& L, int grid, cudaStream_t st, flo
                           rem2d::DevPop p, const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness,
                           int* ticks, int* alive, int* status, unsigned long long* counters, ParkPolicy park, float* park_state,
                           int* park_creature, int* park_count);
+void rem2d_launch_warp_mode(const rem2d::Layout& L, int n, cudaStream_t st, float* slots, const int* order, rem2d::DevPop p,
+                            const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks, int* alive,
+                            int* status, unsigned long long* counters);
 void rem2d_launch_tail(const rem2d::Layout& L, int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot,
                        int n_parked, const rem2d::Terrain* ter, const rem2d::Consts* k, int max_ticks, double* fitness, int* ticks,
                        int* alive, int* status, unsigned long long* counters, unsigned int* tail_trace);
@@ -58,4 +61,5 @@ struct ClassOps {
     template <class... A> void step(A... a) const { rem2d_launch_step(L, a...); }
     template <class... A> void episode(A... a) const { rem2d_launch_episode(L, a...); }
     template <class... A> void tail(A... a) const { rem2d_launch_tail(L, a...); }
+    template <class... A> void warp_mode(A... a) const { rem2d_launch_warp_mode(L, a...); }
 };

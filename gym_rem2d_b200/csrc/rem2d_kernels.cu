@@ -66,7 +66,10 @@ void rem2d_launch_step(const Layout& L, int grid, cudaStream_t st, float* state,
 // mode 1, tail: ONE WARP PER CREATURE for the long-lived creatures that bound the makespan. Lane 0 runs the scalar
 // parts of the tick on the creature's parked column; all 32 lanes share the 180 velocity iterations as a bit-identical
 // dependency wavefront (Sim::wavefront_velocity), which cuts the per-tick latency of a large creature several times.
-// Dynamic shared memory: hot_words * 128 B (bulk) or thot_rows * 128 B + nb version counters (tail).
+// mode 2, warp per creature from tick 0: like mode 1, but the warp builds the world itself. For SMALL populations (every
+// creature gets its own resident warp): the run time is then one creature lifetime at the low tail-mode tick latency
+// instead of one at the bulk latency (pop 1024: ~5x sooner), at 1/32 of the bulk mode's lane efficiency.
+// Dynamic shared memory: hot_words * 128 B (bulk) or thot_rows * 128 B + nb version counters (modes 1, 2).
 __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ Layout L, int mode, float* slots,
                                                         const int* __restrict__ order, int n_order, int* queue, DevPop p,
                                                         const Terrain* __restrict__ ter, const Consts* __restrict__ k, int max_ticks,
@@ -85,7 +88,16 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ 
     const int tail_slot = first_slot + blockIdx.x;
     bool exhausted = false;
     int* ver = (int*)(hot + L.thot_rows * 32);       // tail mode only
-    if (tail) {
+    if (mode == 2) {
+        // whole episode of creature order[blockIdx.x] by this warp: lane 0 builds the world in column blockIdx.x of `slots`
+        my = order[blockIdx.x];
+        sim.g = slots + (size_t)(blockIdx.x >> 5) * L.words * 32 + (blockIdx.x & 31);
+        sim.h = hot;
+        if (lane == 0) sim.build_world(p, my);
+        __syncwarp();
+        sim.nb = sim.Si(S_NB); sim.nj = sim.nb - 1;
+        exhausted = true;
+    } else if (tail) {
         // the slot was allocated by a bulk warp that may still be running: wait until its column has been published
         const int slot = first_slot + blockIdx.x;
         if (lane == 0) {
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ 
         }
         if (tail) my = __shfl_sync(0xffffffffu, my, 0);
     }
-    if (tail && park.tail_trace && lane == 0) {
+    if (mode == 1 && park.tail_trace && lane == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         park.tail_trace[tail_slot * 4 + 2] = (unsigned)(t / 1000ull);
         park.tail_trace[tail_slot * 4 + 3] = (unsigned)loop_iter - 1u;
@@ -192,6 +204,13 @@ void rem2d_launch_episode(const Layout& L, int grid, cudaStream_t st, float* slo
                           unsigned long long* counters, ParkPolicy park, float* park_state, int* park_creature, int* park_count) {
     episode_kernel<<<grid, 32, L.hot_words * 128, st>>>(L, 0, slots, order, n_order, queue, p, ter, k, max_ticks, fitness, ticks, alive,
                                                         status, counters, park, park_state, park_creature, park_count, 0);
+}
+void rem2d_launch_warp_mode(const Layout& L, int n, cudaStream_t st, float* slots, const int* order, DevPop p, const Terrain* ter,
+                            const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
+                            unsigned long long* counters) {
+    ParkPolicy none = {0, 0, 0, 0, 0, nullptr, nullptr};
+    episode_kernel<<<n, 32, (L.thot_rows * 32 + L.nb) * 4, st>>>(L, 2, slots, order, n, nullptr, p, ter, k, max_ticks, fitness, ticks,
+                                                                 alive, status, counters, none, nullptr, nullptr, nullptr, 0);
 }
 void rem2d_launch_tail(const Layout& L, int grid, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked,
                        const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,

@@ -48,8 +48,15 @@ def test_first_100_ticks_bit_exact(enc, flat, n, seed):
         assert_same_state(g.read_state(max_pairs=24), o.read_state(max_pairs=24), "%s after +%d" % (enc, t))
 
 
+# rem2d_run_episodes picks its execution mode by population size: one warp per creature (REM2D_WARP_MODE_MAX, default
+# 24 per SM) for small populations, lane-per-creature bulk warps + tail warps otherwise. Both must equal the oracle.
+BULK, WARP = "0", "1000000"
+
+
+@pytest.mark.parametrize("mode", [BULK, WARP])
 @pytest.mark.parametrize("enc,n,seed", [("direct", 512, 11), ("lsystem", 512, 12), ("ce", 256, 13)])
-def test_full_episode_fitness_identical(enc, n, seed):
+def test_full_episode_fitness_identical(enc, n, seed, mode, monkeypatch):
+    monkeypatch.setenv("REM2D_WARP_MODE_MAX", mode)
     random.seed(seed)
     pop = flatten_population([Individual.random(encoding=enc) for _ in range(n)])
     xs, ys = terrain.generate_terrain()
@@ -91,8 +98,10 @@ def test_single_body_creatures_sleep_and_die_like_the_oracle():
         assert_same_state(g.read_state(max_pairs=8), o.read_state(max_pairs=8), "single-body")
 
 
-def test_episode_kernel_matches_stepping_kernel():
-    """rem2d_run_episodes (persistent kernel, lanes refilled from a queue) vs reset + step on the same GPU."""
+@pytest.mark.parametrize("mode", [BULK, WARP])
+def test_episode_kernel_matches_stepping_kernel(mode, monkeypatch):
+    """rem2d_run_episodes (persistent kernel, lanes refilled from a queue / a warp per creature) vs reset + step."""
+    monkeypatch.setenv("REM2D_WARP_MODE_MAX", mode)
     random.seed(31)
     pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(700)])
     xs, ys = terrain.generate_terrain()
@@ -110,9 +119,11 @@ def test_episode_kernel_matches_stepping_kernel():
     assert (g.read_state()["ticks"] == 3).all()
 
 
-def test_capacity_overflow_is_promoted_to_a_larger_class():
+@pytest.mark.parametrize("mode", [BULK, WARP])
+def test_capacity_overflow_is_promoted_to_a_larger_class(mode, monkeypatch):
     """A terrain with very short edges makes every body overlap dozens of edge proxies: the contact pool of the
     creature's own class overflows and the library must transparently re-run it in a larger class."""
+    monkeypatch.setenv("REM2D_WARP_MODE_MAX", mode)
     random.seed(41)
     pop = flatten_population([Individual.random(encoding="direct") for _ in range(96)])
     ys = np.full(200, 5.0)
@@ -137,6 +148,7 @@ def test_park_cap_and_thresholds_do_not_change_results(monkeypatch):
     o = OracleEngine(threads=8)
     o.set_terrain(ys, K.TERRAIN_STEP)
     fo, to = o.evaluate(pop, 400)
+    monkeypatch.setenv("REM2D_WARP_MODE_MAX", BULK)
     for park in ("8", "64", "0"):
         monkeypatch.setenv("REM2D_PARK_TICKS", park)
         g = Engine(device=0)
@@ -146,9 +158,10 @@ def test_park_cap_and_thresholds_do_not_change_results(monkeypatch):
         assert g.counters() == o.counters(), park
 
 
-def test_config2_direct_flat_1024_and_config4_mixed_cppn_ce():
-    """BASELINE.json configs 2 and 4 at test size: 1024 direct-encoding creatures on flat terrain, and a mixed CPPN / CE
-    population on rough terrain — per-creature fitness and lifetime identical to the oracle."""
+def test_config2_direct_flat_1024_and_config4_mixed_cppn_ce(monkeypatch):
+    """BASELINE.json configs 2 and 4 at test size: 1024 direct-encoding creatures on flat terrain (default mode for this
+    size: a warp per creature), and a mixed CPPN / CE population on rough terrain (forced to the bulk mode) —
+    per-creature fitness and lifetime identical to the oracle."""
     from gym_rem2d_b200.population import random_population
     pop2 = random_population(1024, ("direct",), seed=1, workers=4)
     xs, ys = terrain.flat_terrain()
@@ -158,6 +171,7 @@ def test_config2_direct_flat_1024_and_config4_mixed_cppn_ce():
     assert np.array_equal(tg, to) and np.array_equal(fg, fo)
     pop4 = random_population(768, ("cppn", "ce"), seed=3, workers=4)
     xs, ys = terrain.generate_terrain()
+    monkeypatch.setenv("REM2D_WARP_MODE_MAX", BULK)
     g, o = engines(ys)
     fg, tg = g.evaluate(pop4, K.EVALUATION_STEPS)
     fo, to = o.evaluate(pop4, K.EVALUATION_STEPS)
