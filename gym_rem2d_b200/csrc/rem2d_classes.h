@@ -26,6 +26,8 @@ struct ParkPolicy {
     int late_ticks;   // threshold for creatures pulled from position >= late_from of the class queue (the late starters
     int late_from;    //   bound the makespan: they move to the low-latency kernel sooner)
     int drain_lanes;  // once the queue is empty, a warp with <= this many live lanes parks them all and exits
+    int lead_from;    // lifetime prediction: from this tick on (0: off) a creature whose lead over the wall of death is at
+    float lead;       //   least `lead` (world units; lead / wod_speed = ticks it would survive standing still) is parked
     // diagnostics (REM2D_TRACE=1): every 4th tick lane 0 of each warp records {globaltimer us, live lanes | tick << 8 |
     // smid << 24}; REM2D_TRACE_SAMPLES entries per warp. Null in production.
     unsigned int* trace;

@@ -560,7 +560,7 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
             CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
             g_classes(k).episode(batches, h->user_stream, d_slots, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter, h->d_consts,
-                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, ParkPolicy{0, 0, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr);
+                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, ParkPolicy{0, 0, 0, 0, 0, 0, 0.0f, nullptr, nullptr}, nullptr, nullptr, nullptr);
             h->launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->user_stream));
@@ -668,6 +668,9 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     if (const char* e = getenv("REM2D_PARK_LATE_FROM")) late_frac = atof(e);
     if (const char* e = getenv("REM2D_PARK_CAP")) cap_frac = atof(e);
     if (const char* e = getenv("REM2D_DRAIN_LANES")) drain_lanes = atoi(e);
+    int lead_from = 0; double lead_ticks = 100.0;
+    if (const char* e = getenv("REM2D_PARK_LEAD_FROM")) lead_from = atoi(e);
+    if (const char* e = getenv("REM2D_PARK_LEAD")) lead_ticks = atof(e);
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
     CK(cudaEventRecord(h->ev_start, h->user_stream));
     int rc = fork_streams(h);
@@ -698,6 +701,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         park.ticks = park_ticks < max_ticks ? park_ticks : 0;
         park.cap = std::min(cs.n_members, std::max(32, std::min((int)(h->n_sms * 64 * cap_frac), (int)(cs.n_members * cap_frac))));
         park.late_ticks = park_late; park.late_from = (int)(late_frac * cs.n_members); park.drain_lanes = drain_lanes;
+        park.lead_from = lead_from; park.lead = (float)(lead_ticks * h->cfg.wod_speed);
         park.trace = nullptr; park.tail_trace = nullptr;
         if (getenv("REM2D_TRACE")) {
             const size_t tb = (size_t)std::max(cs.n_members, 1) * 4 * sizeof(unsigned int);

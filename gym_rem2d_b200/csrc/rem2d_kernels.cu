@@ -163,7 +163,11 @@ __global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ 
                 // its partial work must not be counted
                 if (st) sim.cnt = snapshot;
                 my = -1;
-            } else if (!tail && park.ticks > 0 && (t >= park_at || drain) && *(volatile int*)park_count < park.cap) {
+            } else if (!tail && park.ticks > 0 &&
+                       (t >= park_at || drain ||
+                        (park.lead_from > 0 && t >= park.lead_from && k->terminate &&
+                         (double)sim.B(BF_CX, 0) - sim.Sd(S_WOD_LO) >= (double)park.lead)) &&
+                       *(volatile int*)park_count < park.cap) {
                 // long-lived creature: park its state; the latency-oriented tail mode (one warp per creature) finishes it.
                 // (the counter never exceeds the cap: the host hands every counted slot to a tail launch)
                 int slot = -1, seen = *(volatile int*)park_count;
@@ -208,7 +212,7 @@ void rem2d_launch_episode(const Layout& L, int grid, cudaStream_t st, float* slo
 void rem2d_launch_warp_mode(const Layout& L, int n, cudaStream_t st, float* slots, const int* order, DevPop p, const Terrain* ter,
                             const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
                             unsigned long long* counters) {
-    ParkPolicy none = {0, 0, 0, 0, 0, nullptr, nullptr};
+    ParkPolicy none = {0, 0, 0, 0, 0, 0, 0.0f, nullptr, nullptr};
     episode_kernel<<<n, 32, (L.thot_rows * 32 + L.nb) * 4, st>>>(L, 2, slots, order, n, nullptr, p, ter, k, max_ticks, fitness, ticks,
                                                                  alive, status, counters, none, nullptr, nullptr, nullptr, 0);
 }
@@ -216,7 +220,7 @@ void rem2d_launch_tail(const Layout& L, int grid, cudaStream_t st, float* park_s
                        const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
                        unsigned long long* counters, unsigned int* tail_trace) {
     (void)n_parked;      // grid == number of parked creatures handed over
-    ParkPolicy none = {0, 0, 0, 0, 0, nullptr, tail_trace};
+    ParkPolicy none = {0, 0, 0, 0, 0, 0, 0.0f, nullptr, tail_trace};
     episode_kernel<<<grid, 32, (L.thot_rows * 32 + L.nb) * 4, st>>>(L, 1, nullptr, nullptr, 0, nullptr, DevPop(), ter, k, max_ticks, fitness,
                                                                ticks, alive, status, counters, none, park_state, park_creature, nullptr,
                                                                first_slot);

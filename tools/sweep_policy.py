@@ -10,7 +10,7 @@ from gym_rem2d_b200.population import random_population
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 pop = random_population(n, ("lsystem",), seed=2, cache_dir="/tmp/rem2d_cache")
 xs, ys = terrain.generate_terrain()
-KNOBS = ("REM2D_SMALL_WEIGHT", "REM2D_SMEM_BUDGET_KB", "REM2D_PARK_TICKS", "REM2D_PARK_LATE", "REM2D_PARK_LATE_FROM", "REM2D_PARK_CAP", "REM2D_DRAIN_LANES")
+KNOBS = ("REM2D_PARK_LEAD_FROM", "REM2D_PARK_LEAD", "REM2D_SMALL_WEIGHT", "REM2D_SMEM_BUDGET_KB", "REM2D_PARK_TICKS", "REM2D_PARK_LATE", "REM2D_PARK_LATE_FROM", "REM2D_PARK_CAP", "REM2D_DRAIN_LANES")
 
 
 def run(tag, lib=None, **env):
