@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-# The library runs one stream per capacity class (+ one per tail kernel); with the default 8 hardware queues, streams
+# The library runs one stream per capacity class (+ one per tail-mode launch); with the default 8 hardware queues, streams
 # alias and stream-waits block unrelated launches. Must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 

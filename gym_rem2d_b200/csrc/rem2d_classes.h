@@ -1,4 +1,4 @@
-// rem2d_classes.h — capacity classes and the launch interface of the four kernels (rem2d_kernels.cu; one translation
+// rem2d_classes.h — capacity classes and the launch interface of the three kernels (rem2d_kernels.cu; one translation
 // unit per kernel so that they compile in parallel). All classes run the SAME code: the class only selects a Layout.
 #pragma once
 #include <cuda_runtime.h>
@@ -19,7 +19,7 @@
     X(8, 44, 192, 10)
 #define N_CLASSES 9
 
-// When the bulk (lane-per-creature) episode kernel hands a creature over to the warp-per-creature tail kernel.
+// When the bulk (lane-per-creature) episode kernel hands a creature over to the warp-per-creature tail mode (launches of the same kernel).
 struct ParkPolicy {
     int ticks;        // park a creature that is still alive after this many ticks (0: never park)
     int cap;          // at most this many creatures of the class are parked

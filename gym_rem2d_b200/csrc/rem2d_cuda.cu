@@ -1,9 +1,11 @@
-// rem2d_cuda.cu — kernels + C-ABI (include/rem2d.h) of the CUDA build, sm_100a only.
+// rem2d_cuda.cu — host side + C-ABI (include/rem2d.h) of the CUDA build, sm_100a only (kernels: rem2d_kernels.cu).
 //
-// Host side: sorts creatures into capacity classes (by body count), packs them 32 per batch, keeps one
-// lane-interleaved state block per batch in HBM and launches one CTA (one warp) per batch on one
-// stream per class so small and large classes overlap on the 148 SMs. There is no CPU physics
-// fallback: every tick is computed by rem2d::Sim<...>::tick on the device.
+// Sorts creatures into capacity classes (by body count), keeps one lane-interleaved state block per 32 creatures in
+// HBM, and runs every class on its own stream so small and large classes overlap on the 148 SMs: rem2d_step on a
+// static creature -> lane mapping, rem2d_run_episodes / rem2d_evaluate on persistent warps that pull creatures from a
+// per-class queue (bulk mode), hand long-lived creatures to warp-per-creature launches (tail mode), or give every
+// creature its own warp when the population is small. There is no CPU physics fallback: every tick is computed by
+// rem2d::Sim::tick on the device.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -139,7 +141,7 @@ struct rem2d_handle {
     Terrain* d_ter = nullptr;
     Consts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;
-    // Tail kernels are launched on demand, each on a stream of this pool that is idle at that moment: a tail kernel lives as
+    // Tail-mode launches are made on demand, each on a stream of this pool that is idle at that moment: a tail launch lives as
     // long as its longest creature (hundreds of ms), so a second kernel queued behind it on the same stream would wait for
     // it (and block its hardware queue for other streams). The pool grows when no stream is idle.
     std::vector<cudaStream_t> tail_pool;
@@ -654,7 +656,7 @@ static int launch_phased(rem2d_handle* h, int max_ticks) {
 // Whole episodes for the uploaded population on the persistent episode kernels (one per class, concurrent).
 static int launch_episodes(rem2d_handle* h, int max_ticks) {
     if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
-    // creatures still alive after park_ticks are finished by the tail kernel (REM2D_PARK_TICKS=0 disables parking)
+    // creatures still alive after park_ticks are finished by tail-mode launches (REM2D_PARK_TICKS=0 disables parking)
     // Measured on B200 (tools/sweep_policy.py, 65536 L-system creatures): parking at 256 ticks (~0.5 % of the creatures) is
     // the best trade: a tail warp finishes a creature 3-4x sooner than its bulk lane would, but it occupies a whole warp, so
     // earlier thresholds (thousands of parked creatures) slow the bulk down more than they shorten the critical path; later
@@ -723,7 +725,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     CK(cudaGetLastError());
     if (park_ticks > 0 && park_ticks < max_ticks) {
         // Tail: while the episode kernels run, poll their park counters and hand newly parked creatures to the
-        // warp-per-creature tail kernel right away (pool of streams), so the sequential ticks of the longest-lived
+        // warp-per-creature tail mode right away (pool of streams), so the sequential ticks of the longest-lived
         // creatures overlap the bulk instead of extending the run; the last launch of a class happens when its episode
         // kernel has finished.
         bool running[N_CLASSES];

@@ -1530,7 +1530,7 @@ struct Sim {
     }
 
     // ---- Modular2D.step + the body of evaluate()'s loop, in three parts so that a whole warp can take over the velocity
-    // iterations of one creature (tail kernel): tick_pre -> [solve_velocity | wavefront_velocity] -> tick_post.
+    // iterations of one creature (tail mode): tick_pre -> [solve_velocity | wavefront_velocity] -> tick_post.
     // b2World::Step = FindNewContacts (first step) -> Collide -> Solve -> SolveTOI.
     __device__ bool tick_pre(int& nt) {
         double wod = Sd(S_WOD_LO) + k->wod_speed;
@@ -1584,7 +1584,7 @@ struct Sim {
         tick_post(solved, nt);
     }
 
-    // ---- velocity iterations of ONE creature by a whole warp (tail kernel): a dependency-respecting wavefront.
+    // ---- velocity iterations of ONE creature by a whole warp (tail mode): a dependency-respecting wavefront.
     // Box2D's sequential order within an iteration is: joints in island order, then contacts (newest first); two
     // constraints commute exactly iff they share no body. Lane l owns constraints l and l+32 of that sequence; a per-body
     // version counter says how many solves have been applied to the body, and a constraint of iteration `it` may run as

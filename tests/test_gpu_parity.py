@@ -139,7 +139,7 @@ def test_capacity_overflow_is_promoted_to_a_larger_class(mode, monkeypatch):
 
 
 def test_park_cap_and_thresholds_do_not_change_results(monkeypatch):
-    """The tail kernel (warp-per-creature wavefront) is an execution strategy: whatever the park threshold, results
+    """The tail mode (warp-per-creature wavefront) is an execution strategy: whatever the park threshold, results
     must be identical to the oracle. A threshold of 8 ticks with 300 creatures exceeds the park cap of small classes,
     so both the parked and the not-parked continuation are exercised."""
     random.seed(51)
