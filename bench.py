@@ -32,8 +32,9 @@ from gym_rem2d_b200 import terrain  # noqa: E402
 from gym_rem2d_b200.population import random_population  # noqa: E402
 
 METRIC = "creature-steps/sec"
-WORKLOAD = "pop 65536 L-system creatures (1-21 modules), rough BipedalWalker-style terrain (env.seed(4)), " \
+WORKLOAD = "pop %d %s creatures (1-21 modules), rough BipedalWalker-style terrain (env.seed(4)), " \
            "full episodes with wall-of-death termination, dt 1/50, 180 velocity + 60 position iterations"
+ENC_NAMES = {"lsystem": "L-system", "direct": "direct-encoding", "ce": "cellular-encoding", "cppn": "CPPN"}
 
 
 def flops_from_counters(c):
@@ -119,7 +120,7 @@ def main():
     cores = os.cpu_count() or 1
     cache = os.environ.get("REM2D_CACHE", "/tmp/rem2d_cache")
     encodings = tuple(args.encoding.split(","))
-    config = {"workload": WORKLOAD, "population_per_gpu": args.pop, "population_total": args.pop * max(world, 1),
+    config = {"workload": WORKLOAD % (args.pop, "/".join(ENC_NAMES.get(e, e) for e in encodings)), "population_per_gpu": args.pop, "population_total": args.pop * max(world, 1),
               "encoding": args.encoding, "terrain": "rough seed 4", "episode": "full (WOD on, <= 10000 ticks)",
               "l2_policy": "state blocks (>= 0.5 GB per 65536 creatures) exceed the 126 MB L2; no explicit flush",
               "shard": "by individual, one shard per rank, fitness all_gather over NCCL"}
