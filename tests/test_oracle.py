@@ -200,3 +200,95 @@ def test_counters_and_threads_are_consistent():
     assert res[0][2] == res[1][2]
     assert res[0][2]["ticks"] == int(res[0][1].sum())
     assert np.all(res[0][1] >= 40)     # the wall of death reaches x = 5 at tick 125; creatures pushed backwards die earlier
+
+
+def test_jointed_free_fall_conserves_linear_and_angular_momentum():
+    """Internal constraint impulses (point-to-point, motor, limit) are equal and opposite: while a driven 3-body chain is in
+    free fall, its centre of mass follows the closed-form trajectory of a single body, its horizontal momentum stays zero
+    and its angular momentum about the centre of mass stays at its initial value (zero) — independent of what the
+    controllers do. Checks the sign conventions and lever arms of the restated revolute solver (velocity AND position
+    phase: the position solver moves bodies without touching velocities, so the centre of mass must not move either)."""
+    e = flat_engine(terminate=0)
+
+    def place(parent_pose, anchor_a, angle, anchor_b):       # child centre such that the two anchors coincide
+        px, py, pa = parent_pose
+        ax = px + math.cos(pa) * anchor_a[0] - math.sin(pa) * anchor_a[1]
+        ay = py + math.sin(pa) * anchor_a[0] + math.cos(pa) * anchor_a[1]
+        return (ax - (math.cos(angle) * anchor_b[0] - math.sin(angle) * anchor_b[1]),
+                ay - (math.sin(angle) * anchor_b[0] + math.cos(angle) * anchor_b[1]), angle)
+
+    c = single(0, 0.5, 0.5, y=60.0)
+    p1 = place((5.0, 60.0, 0.0), (0.0, 0.0), 0.3, (0.0, 0.4))
+    add_child(c, 0, 0, 0.1, 0.4, p1[0], p1[1], 0.3, (0.0, 0.0), (0.0, 0.4), (1.2, 0.5, 0.35, 0.2, 0.0))
+    p2 = place(p1, (0.0, -0.4), -0.2, (0.3, 0.0))
+    add_child(c, 1, 0, 0.3, 0.15, p2[0], p2[1], -0.2, (0.0, -0.4), (0.3, 0.0), (0.9, 1.5, 0.5, -0.3, 0.0))
+    e.upload(pack([c]))
+    hx, hy = np.array(c.hx), np.array(c.hy)
+    m = K.MODULE_DENSITY * 4.0 * hx * hy                                  # b2PolygonShape::ComputeMass of a box
+    inertia = m * ((2 * hx) ** 2 + (2 * hy) ** 2) / 12.0
+    st = e.read_state()
+    com0 = (m[:, None] * st["pose"][:, :2].astype(np.float64)).sum(0) / m.sum()
+    moved = False
+    for k in range(1, 41):
+        e.step(1)
+        st = e.read_state()
+        p, v = st["pose"].astype(np.float64), st["vel"].astype(np.float64)
+        assert st["n_contacts"][0] == 0
+        com = (m[:, None] * p[:, :2]).sum(0) / m.sum()
+        vcom = (m[:, None] * v[:, :2]).sum(0) / m.sum()
+        assert abs(com[0] - com0[0]) < 2e-5 and abs(vcom[0]) < 2e-5
+        assert abs(com[1] - (com0[1] - 10.0 * 0.02 ** 2 * k * (k + 1) / 2)) < 2e-4
+        assert abs(vcom[1] + 10.0 * 0.02 * k) < 2e-5
+        r = p[:, :2] - com
+        u = v[:, :2] - vcom
+        L = (inertia * v[:, 2]).sum() + (m * (r[:, 0] * u[:, 1] - r[:, 1] * u[:, 0])).sum()
+        assert abs(L) < 5e-4, (k, L)
+        moved |= abs(st["pose"][1, 2] - st["pose"][0, 2] - 0.3) > 0.05
+    assert moved                                                           # the motors did drive the joints
+
+
+def test_motor_cannot_push_a_joint_through_its_limit():
+    """A controller offset of 2.5 rad asks for an angle beyond the +pi/2 joint limit: the P-controlled motor drives the joint
+    into the limit, where the 3x3 (point + limit) solve and the position solver hold it within the angular slop."""
+    e = flat_engine(terminate=0)
+    c = _pendulum((0.0, 0.0, 0.0, 2.5, 0.0))
+    e.upload(pack([c]))
+    seen_limit = False
+    for k in range(60):
+        e.step(1)
+        st = e.read_state()
+        rel = float(st["pose"][1, 2]) - float(st["pose"][0, 2])
+        assert rel <= math.pi / 2 + 2.0 * (2.0 / 180.0 * math.pi) + 1e-6, (k, rel)
+        seen_limit |= st["limit_state"][0] == 2
+    assert seen_limit and rel > math.pi / 2 - 0.1                     # it got there and stays there
+    # Box2D's convention: the impulse of an active UPPER limit is <= 0. In the steady state it balances the saturated motor
+    # (+dt * maxMotorTorque = 0.02 * 50) exactly, because nothing else exerts a torque about the joint in free fall.
+    assert st["joint_impulse"][0, 3] == F32(0.02) * F32(50.0)
+    assert st["joint_impulse"][0, 2] <= 0.0 and abs(float(st["joint_impulse"][0, 2]) + 1.0) < 1e-3
+
+
+@pytest.mark.parametrize("tan_slope", [0.3, 0.45, 0.6, 1.0])
+def test_coulomb_friction_on_an_incline(tan_slope):
+    """A box on an inclined edge chain: b2MixFriction gives mu = sqrt(2.5 * 0.1) = 0.5, so the box sticks while
+    tan(theta) < 0.5 and otherwise slides with a = g (sin(theta) - mu cos(theta)) — friction clamp against the accumulated
+    normal impulse, manifold ids across collinear edges and warm starting all have to be right for this to come out."""
+    th = math.atan(tan_slope)
+    xs = np.arange(200) * K.TERRAIN_STEP
+    e = OracleEngine(terminate=0, allow_sleep=0)
+    e.set_terrain(60.0 - tan_slope * xs, K.TERRAIN_STEP)
+    x0, hx, hy = 10.0, 0.5, 0.25
+    d = hy + 0.02                                                      # just above the surface, aligned with it
+    cx, cy = x0 + math.sin(th) * d, 60.0 - tan_slope * x0 + math.cos(th) * d
+    e.upload(pack([single(0, hx, hy, x=cx, y=cy, a=-th)]))
+    v_along = []
+    for k in range(101):
+        e.step(1)
+        st = e.read_state()
+        v_along.append(float(st["vel"][0, 0]) * math.cos(th) - float(st["vel"][0, 1]) * math.sin(th))
+    accel = (v_along[100] - v_along[40]) / (60 * 0.02)
+    expected = max(0.0, 10.0 * (math.sin(th) - 0.5 * math.cos(th)))
+    if expected == 0.0:
+        assert abs(v_along[100]) < 1e-4 and abs(float(st["pose"][0, 0]) - cx) < 2e-3
+    else:
+        assert abs(accel - expected) < 0.01 * expected + 1e-3, (accel, expected)
+    assert abs(float(st["pose"][0, 2]) + th) < 0.01                    # it slides, it does not tumble
