@@ -177,3 +177,22 @@ def test_config2_direct_flat_1024_and_config4_mixed_cppn_ce(monkeypatch):
     fo, to = o.evaluate(pop4, K.EVALUATION_STEPS)
     assert np.array_equal(tg, to) and np.array_equal(fg, fo)
     assert g.counters() == o.counters()
+
+
+@pytest.mark.parametrize("tan_slope", [0.6, -0.35])
+def test_inclined_terrain_and_no_sleep_bit_exact(tan_slope):
+    """Edge chains that are not axis-aligned (sliding and tumbling creatures, manifolds across collinear edges, bodies that
+    start inside the slope) with sleeping disabled and a fixed horizon: state after every block of ticks identical to the
+    oracle."""
+    random.seed(61)
+    pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(160)])
+    xs = np.arange(200) * K.TERRAIN_STEP
+    x_start = K.TERRAIN_STEP * K.TERRAIN_STARTPAD / 2          # creatures are built around (x_start, TERRAIN_HEIGHT + 2)
+    ys = K.TERRAIN_HEIGHT - tan_slope * (xs - x_start)
+    g, o = Engine(device=0, terminate=0, allow_sleep=0), OracleEngine(threads=8, terminate=0, allow_sleep=0)
+    for e in (g, o):
+        e.set_terrain(ys, K.TERRAIN_STEP)
+    g.upload(pop); o.upload(pop)
+    for t in (20, 40, 60, 80):
+        g.step(t); o.step(t)
+        assert_same_state(g.read_state(max_pairs=16), o.read_state(max_pairs=16), "incline %.2f after +%d" % (tan_slope, t))
