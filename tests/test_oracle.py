@@ -4,7 +4,8 @@
   frozen fake Box2D world (tests/golden/control_pin.json)                               (a9, a10, a12)
 * analytic known answers for the Box2D-2.3 restatement (pin P3): free fall, resting
   contact depth and manifold, interior-vertex circle contacts, motor torque saturation, limit snap,
-  sleeping, wall-of-death lifetime.
+  sleeping, wall-of-death lifetime, momentum conservation, Coulomb friction and rolling on inclines,
+  time of impact.
 The oracle is parity-UNPINNED against real pybox2d (not installable); these tests pin what can be.
 """
 import json
@@ -292,3 +293,44 @@ def test_coulomb_friction_on_an_incline(tan_slope):
     else:
         assert abs(accel - expected) < 0.01 * expected + 1e-3, (accel, expected)
     assert abs(float(st["pose"][0, 2]) + th) < 0.01                    # it slides, it does not tumble
+
+
+def test_time_of_impact_stops_a_fast_small_body_at_the_edge_chain():
+    """Continuous collision: a circle of radius 0.1 dropped from 55 m above the (zero-thickness) edge chain moves 0.66 m per
+    tick when it arrives; the discrete step alone would put it below the terrain. SolveTOI must stop it at the surface."""
+    e = flat_engine(terminate=0)
+    e.upload(pack([single(1, 0.1, 0.1, x=5.1, y=60.0)]))
+    lowest, events = 1e9, 0
+    for k in range(260):
+        e.step(1)
+        st = e.read_state()
+        lowest = min(lowest, float(st["pose"][0, 1]))
+    events = e.counters()["toi_events"]
+    assert events >= 1
+    assert lowest > K.TERRAIN_HEIGHT + 0.1 - 3 * 0.005 - 1e-4          # never deeper than the TOI target separation
+    assert abs(float(st["pose"][0, 1]) - (K.TERRAIN_HEIGHT + 0.1)) < 0.011 and abs(float(st["vel"][0, 1])) < 1e-3   # at rest on it
+
+
+@pytest.mark.parametrize("tan_slope", [0.3, 1.0, 2.0])
+def test_disc_rolls_without_slipping_until_the_slope_exceeds_three_mu(tan_slope):
+    """A disc (I = m r^2 / 2) on an incline rolls with a = 2/3 g sin(theta) and v = omega r as long as tan(theta) < 3 mu = 1.5;
+    on a steeper slope the contact slips and the centre accelerates like a sliding body. Pins the circle mass data, the
+    edge-circle manifold, and the friction impulse acting at the contact point (torque as well as force)."""
+    th = math.atan(tan_slope)
+    xs = np.arange(200) * K.TERRAIN_STEP
+    e = OracleEngine(terminate=0, allow_sleep=0)
+    e.set_terrain(80.0 - tan_slope * xs, K.TERRAIN_STEP)
+    r, x0 = 0.25, 6.0
+    cx, cy = x0 + math.sin(th) * (r + 0.005), 80.0 - tan_slope * x0 + math.cos(th) * (r + 0.005)
+    e.upload(pack([single(1, r, r, x=cx, y=cy)]))
+    v = []
+    for k in range(101):
+        e.step(1)
+        st = e.read_state()
+        v.append((float(st["vel"][0, 0]) * math.cos(th) - float(st["vel"][0, 1]) * math.sin(th), float(st["vel"][0, 2])))
+    accel = (v[100][0] - v[40][0]) / (60 * 0.02)
+    slip_ratio = v[100][0] / (-v[100][1] * r)
+    if tan_slope < 1.5:
+        assert abs(accel - 10.0 * math.sin(th) * 2.0 / 3.0) < 0.01 * accel and abs(slip_ratio - 1.0) < 0.01
+    else:
+        assert abs(accel - 10.0 * (math.sin(th) - 0.5 * math.cos(th))) < 0.02 * accel and slip_ratio > 1.2
