@@ -665,6 +665,13 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     // long, the rest simply stay on their lanes.
     int park_ticks = 256, park_late = 256, drain_lanes = 0;
     double late_frac = 1.0, cap_frac = 1.0 / 16.0;
+    {   // Under-filled GPU (every creature of every class has a lane from the start, e.g. 16384 creatures): tail warps find
+        // free SM resources, so parking earlier pays (16384 creatures: 450 -> 413 ms with 160 ticks and a quarter of a class).
+        bool single_round = true;
+        for (int k = 0; k < N_CLASSES; ++k)
+            if (h->cls[k].n_batches && h->cls[k].episode_grid < h->cls[k].n_batches) single_round = false;
+        if (single_round) { park_ticks = park_late = 160; cap_frac = 0.25; }
+    }
     if (const char* e = getenv("REM2D_PARK_TICKS")) park_ticks = park_late = atoi(e);
     if (const char* e = getenv("REM2D_PARK_LATE")) park_late = atoi(e);
     if (const char* e = getenv("REM2D_PARK_LATE_FROM")) late_frac = atof(e);
