@@ -99,7 +99,7 @@ def cpu_baseline(pop, ys, sample_creatures, threads):
     t0 = time.perf_counter()
     fit, ticks = e.evaluate(sub, K.EVALUATION_STEPS)
     dt = time.perf_counter() - t0
-    return float(ticks.sum()) / dt, dt, sub.n_creatures, int(ticks.sum())
+    return float(ticks.sum()) / dt, dt, sub.n_creatures, int(ticks.sum()), fit, ticks
 
 
 def main():
@@ -134,7 +134,7 @@ def main():
         pop = random_population(sample, encodings, seed=args.seed, workers=max(1, cores // 2), cache_dir=cache)
         vals = []
         for i in range(args.warmup + args.steps):
-            v, dt, n, cs = cpu_baseline(pop, ys, sample, cores)
+            v, dt, n, cs, _, _ = cpu_baseline(pop, ys, sample, cores)
             if i >= args.warmup:
                 vals.append((v, dt))
         value = float(np.mean([v for v, _ in vals])) if vals else 0.0
@@ -191,6 +191,7 @@ def main():
     launches = eng.launch_count() - l0
     counters = eng.counters()          # of the last evaluation
     fit = eng.fitness()
+    ticks_gpu = eng.ticks()
     creature_steps = counters["ticks"]
     t = torch.tensor([ms_total, float(creature_steps)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -263,11 +264,20 @@ def main():
                 "mean_ticks_per_creature": creature_steps / pop.n_creatures}
         if not args.no_cpu_baseline and world == 1:
             sample = min(args.pop, max(256, 1800 * cores))      # ~10 s of CPU work
-            v, dt, n, cs = cpu_baseline(pop, ys, sample, cores)
+            v, dt, n, cs, fit_cpu, ticks_cpu = cpu_baseline(pop, ys, sample, cores)
+            # parity of the benchmarked configuration: the oracle's per-creature fitness and lifetime of the sampled
+            # creatures against what the timed GPU run (device-resident leg) and the e2e leg returned, bit for bit
+            bad = int(np.count_nonzero((fit[:n] != fit_cpu) | (ticks_gpu[:n] != ticks_cpu)))
+            bad_e2e = int(np.count_nonzero((f2[:n] != fit_cpu) | (tk[:n] != ticks_cpu)))
+            line["parity"] = {"n": int(n), "mismatches": bad, "mismatches_e2e": bad_e2e,
+                              "checked": "fitness (float64) and ticks of the first n creatures, exact equality vs oracle"}
             line["cpu_baseline"] = {"value": v, "unit": "creature-steps/s", "cores": cores, "kind": "port",
                                     "sample": "first %d creatures of the same population, whole episodes, %.1f s; pybox2d is not "
                                               "installable: float32 C restatement oracle/rem2d_oracle.c" % (n, dt)}
         print(json.dumps(line))
+        if line.get("parity", {}).get("mismatches", 0) or line.get("parity", {}).get("mismatches_e2e", 0):
+            sys.stderr.write("bench: GPU results differ from the oracle on the benchmarked configuration\n")
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 

@@ -196,3 +196,83 @@ def test_inclined_terrain_and_no_sleep_bit_exact(tan_slope):
     for t in (20, 40, 60, 80):
         g.step(t); o.step(t)
         assert_same_state(g.read_state(max_pairs=16), o.read_state(max_pairs=16), "incline %.2f after +%d" % (tan_slope, t))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The PRODUCTION execution path at test size: persistent bulk warps whose lanes are REFILLED from the
+# class queue (episode_grid < n_batches), parking at 256 ticks with a 1/16 cap and on-demand tail launches that see
+# late-parked creatures. A small shared-memory budget forces several refill rounds with a few thousand creatures.
+def _oracle_eval(pop, ys, steps=K.EVALUATION_STEPS, **cfg):
+    o = OracleEngine(threads=max(8, (__import__("os").cpu_count() or 8)), **cfg)
+    o.set_terrain(ys, K.TERRAIN_STEP)
+    fo, to = o.evaluate(pop, steps)
+    return fo, to, o.counters()
+
+
+@pytest.mark.parametrize("budget_kb,park", [("24", None), ("40", "140"), ("16", "256")])
+def test_lane_refill_rounds_and_late_parking_match_the_oracle(budget_kb, park, monkeypatch):
+    from gym_rem2d_b200.population import random_population
+    pop = random_population(3072, ("lsystem",), seed=71, workers=4)
+    xs, ys = terrain.generate_terrain()
+    fo, to, co = _oracle_eval(pop, ys)
+    monkeypatch.setenv("REM2D_WARP_MODE_MAX", "0")
+    monkeypatch.setenv("REM2D_SMEM_BUDGET_KB", budget_kb)      # per-SM budget: every class gets fewer warps than batches
+    if park is not None:
+        monkeypatch.setenv("REM2D_PARK_TICKS", park)
+        monkeypatch.setenv("REM2D_PARK_CAP", "0.0625")
+    g = Engine(device=0)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to), "ticks differ for %d creatures" % (tg != to).sum()
+    assert np.array_equal(fg, fo)
+    assert g.counters() == co
+    assert (to > 256).sum() >= 3, "the population must contain creatures that outlive the park threshold"
+    # same handle, second evaluation (buffers and queues are reused)
+    fg2, tg2 = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg2, to) and np.array_equal(fg2, fo)
+
+
+@pytest.mark.parametrize("terminate", [1, 0])
+def test_config1_single_creature_1000_ticks(terminate):
+    """BASELINE config 1: ONE direct-encoding creature (seed 0), flat terrain, 1000 ticks with the termination rule on and
+    off — state after every 100 ticks and the episode result identical to the oracle."""
+    random.seed(0)
+    np.random.seed(0)
+    pop = flatten_population([Individual.random(encoding="direct")])
+    xs, ys = terrain.flat_terrain()
+    g, o = engines(ys, terminate=terminate)
+    g.upload(pop); o.upload(pop)
+    for _ in range(10):
+        g.step(100); o.step(100)
+        assert_same_state(g.read_state(max_pairs=24), o.read_state(max_pairs=24), "config 1, terminate=%d" % terminate)
+    if not terminate:
+        assert (g.read_state()["ticks"] == 1000).all()
+    fg, tg = g.evaluate(pop, 1000)
+    fo, to = o.evaluate(pop, 1000)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo)
+
+
+def test_config3_16384_lsystem_rough_full_size():
+    """BASELINE config 3 at its stated size: 16384 L-system creatures (seed 2), rough terrain, whole episodes in the default
+    execution mode for this size (bulk warps, under-filled GPU -> park at 160 ticks)."""
+    from gym_rem2d_b200.population import random_population
+    pop = random_population(16384, ("lsystem",), seed=2, workers=8)
+    xs, ys = terrain.generate_terrain()
+    fo, to, co = _oracle_eval(pop, ys)
+    g = Engine(device=0)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo)
+    assert g.counters() == co
+
+
+def test_config4_4096_cppn_ce_rough():
+    from gym_rem2d_b200.population import random_population
+    pop = random_population(4096, ("cppn", "ce"), seed=3, workers=8)
+    xs, ys = terrain.generate_terrain()
+    fo, to, co = _oracle_eval(pop, ys)
+    g = Engine(device=0)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo)
+    assert g.counters() == co
