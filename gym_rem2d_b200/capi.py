@@ -87,6 +87,8 @@ def load_library(path=None):
     lib.rem2d_measure_fp32_peak.argtypes = [H, C.POINTER(C.c_double)]
     lib.rem2d_launch_count.argtypes = [H]
     lib.rem2d_launch_count.restype = C.c_int64
+    lib.rem2d_set_option.argtypes = [H, C.c_char_p, C.c_double]
+    lib.rem2d_read_roots.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     _LIBS[path] = lib
     return lib
 
@@ -207,6 +209,17 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.rem2d_launch_count(self.h))
+
+    def set_option(self, name, value):
+        """Execution-strategy option (never changes results): see include/rem2d.h, rem2d_set_option."""
+        self._check(self.lib.rem2d_set_option(self.h, name.encode(), float(value)), "rem2d_set_option(%s)" % name)
+
+    def read_roots(self):
+        """(root x float32[n], wall-of-death position float64[n], alive int32[n]) — what a step-wise driver needs per tick."""
+        n = self.pop.n_creatures
+        x, wod, alive = np.zeros(n, np.float32), np.zeros(n, np.float64), np.zeros(n, np.int32)
+        self._check(self.lib.rem2d_read_roots(self.h, _ptr(x), _ptr(wod), _ptr(alive)), "rem2d_read_roots")
+        return x, wod, alive
 
     def read_state(self, max_pairs=0):
         pop = self.pop

@@ -17,12 +17,13 @@
 #include <vector>
 
 #include "rem2d_classes.h"
+#include "rem2d_host_util.h"
 
 using namespace rem2d;
 
 // ------------------------------------------------------------------ capacity classes (rem2d_classes.h)
 static const ClassOps g_classes_tab[N_CLASSES] = {
-#define X(i, NB, NC, NT) ClassOps(NB, NC, NT),
+#define X(i, NB, NC, NT, GS) ClassOps(NB, NC, NT, GS),
     REM2D_CLASSES(X)
 #undef X
 };
@@ -40,6 +41,19 @@ __global__ void gather_kernel(const float* state, const int* __restrict__ lane_c
     ticks[c] = __float_as_int(g[S_TICKS * 32]);
     alive[c] = __float_as_int(g[S_ALIVE * 32]);
     status[c] = __float_as_int(g[S_STATUS * 32]);
+}
+
+// root x / wall of death / alive of every creature of a class -> creature-indexed outputs (rem2d_read_roots)
+__global__ void roots_kernel(const float* state, const int* __restrict__ lane_creature, int n_lanes, int words,
+                             float* root_x, double* wod, int* alive) {
+    int gl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= n_lanes) return;
+    int c = lane_creature[gl];
+    if (c < 0) return;
+    const float* g = state + (size_t)(gl >> 5) * words * 32 + (gl & 31);
+    root_x[c] = g[(S_COUNT + BF_CX) * 32];
+    wod[c] = __hiloint2double(__float_as_int(g[S_WOD_HI * 32]), __float_as_int(g[S_WOD_LO * 32]));
+    alive[c] = __float_as_int(g[S_ALIVE * 32]);
 }
 
 // ---- survivor compaction between tick phases of the evaluate path -------------------------------------------------
@@ -118,6 +132,7 @@ struct ClassState {
     int* d_lane_creature = nullptr;
     int* d_queue = nullptr;
     Buf b_state, b_state2, b_lc, b_lcw0, b_lcw1, b_dst, b_small, b_trace, b_ttrace;   // backing storage (grow-only)
+    Buf b_redo_order, b_redo_slots;     // promotion re-runs (grow-only)
     // phased evaluation with survivor compaction (ping-pong buffers)
     float* d_state2 = nullptr;
     int* d_lc_work[2] = {nullptr, nullptr};   // lane -> creature maps of the compacted phases (d_lane_creature stays the static map)
@@ -135,8 +150,23 @@ struct ClassState {
     cudaEvent_t t_begin = nullptr, t_end = nullptr;     // per-class timeline of the last rem2d_run_episodes (diagnostics)
 };
 
+// Tuning / diagnostic options (rem2d_set_option; the REM2D_* environment variables of the same names are read ONCE, at
+// rem2d_create, as initial values - tools/sweep_policy.py and the tests use them). Defaults are the measured optimum.
+struct Options {
+    int warp_mode_max = -1;      // largest population that runs one warp per creature from tick 0 (-1: 48 per SM)
+    int park_ticks = -1;         // park threshold of the queue mode (-1: automatic, 0: never park)
+    double park_cap = -1.0;      // fraction of a class that may be parked (-1: automatic)
+    double smem_budget_kb = 227.0, small_weight = 1.0;
+    int min_class = 0;
+    int group_shift = -1;        // log2 lanes per creature in the queue / step kernels (-1: per class default)
+    int tail_group_shift = 5;    // log2 lanes per creature of the tail launches
+    int trace = 0;
+    int phased = 0;              // tick phases with survivor compaction instead of the persistent queue kernel
+};
+
 struct rem2d_handle {
     rem2d_config cfg;
+    Options opt;
     cudaStream_t user_stream = nullptr;
     Terrain* d_ter = nullptr;
     Consts* d_consts = nullptr;
@@ -159,7 +189,7 @@ struct rem2d_handle {
     std::vector<int32_t> body_off;
     std::vector<int> creature_class, creature_lane;     // lane index within the class (batch*32+lane)
     Buf d_pop_mem[16];
-    Buf b_results;
+    Buf b_results, b_roots;
     DevPop dpop{};
     ClassState cls[N_CLASSES];
     double* d_fitness = nullptr; int *d_ticks = nullptr, *d_alive = nullptr, *d_status = nullptr;
@@ -183,6 +213,36 @@ static thread_local std::string g_create_err;
         }                                                                                                \
     } while (0)
 
+static int class_gs(const rem2d_handle* h, int k) {
+    int gs = h->opt.group_shift >= 0 ? h->opt.group_shift : g_classes(k).gs;
+    return gs < 0 ? 0 : (gs > 5 ? 5 : gs);
+}
+static bool set_option(Options& o, const char* name, double v) {
+    const std::string n(name);
+    if (n == "warp_mode_max") o.warp_mode_max = (int)v;
+    else if (n == "park_ticks") o.park_ticks = (int)v;
+    else if (n == "park_cap") o.park_cap = v;
+    else if (n == "smem_budget_kb") o.smem_budget_kb = v;
+    else if (n == "small_weight") o.small_weight = v;
+    else if (n == "min_class") o.min_class = std::max(0, std::min(N_CLASSES - 1, (int)v));
+    else if (n == "group_shift") o.group_shift = (int)v;
+    else if (n == "tail_group_shift") o.tail_group_shift = std::max(0, std::min(5, (int)v));
+    else if (n == "trace") o.trace = (int)v;
+    else if (n == "phased") o.phased = (int)v;
+    else return false;
+    return true;
+}
+static void options_from_env(Options& o) {
+    static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "smem_budget_kb", "small_weight", "min_class",
+                                  "group_shift", "tail_group_shift", "trace"};
+    for (const char* n : names) {
+        std::string env = "REM2D_";
+        for (const char* q = n; *q; ++q) env += (char)toupper(*q);
+        if (const char* e = getenv(env.c_str())) set_option(o, n, atof(e));
+    }
+    if (const char* e = getenv("REM2D_EPISODE_MODE")) o.phased = !strcmp(e, "phased");
+}
+
 static void free_population(rem2d_handle* h) {          // logical reset; the buffers stay allocated for reuse
     for (auto& c : h->cls) { c.n_batches = 0; c.n_members = 0; c.lane_creature.clear(); }
     h->have_pop = false; h->state_valid = false; h->results_valid = false;
@@ -190,13 +250,16 @@ static void free_population(rem2d_handle* h) {          // logical reset; the bu
 static void release_buffers(rem2d_handle* h) {
     for (auto& b : h->d_pop_mem) { if (b.p) cudaFree(b.p); b = Buf(); }
     for (auto& c : h->cls) {
-        Buf* bufs[] = {&c.b_state, &c.b_state2, &c.b_lc, &c.b_lcw0, &c.b_lcw1, &c.b_dst, &c.b_small, &c.b_trace, &c.b_ttrace};
+        Buf* bufs[] = {&c.b_state, &c.b_state2, &c.b_lc, &c.b_lcw0, &c.b_lcw1, &c.b_dst, &c.b_small, &c.b_trace, &c.b_ttrace,
+                       &c.b_redo_order, &c.b_redo_slots};
         for (Buf* b : bufs) { if (b->p) cudaFree(b->p); *b = Buf(); }
         if (c.h_n_alive) cudaFreeHost(c.h_n_alive);
         c.h_n_alive = nullptr;
     }
     if (h->b_results.p) cudaFree(h->b_results.p);
     h->b_results = Buf();
+    if (h->b_roots.p) cudaFree(h->b_roots.p);
+    h->b_roots = Buf();
 }
 
 extern "C" {
@@ -238,39 +301,43 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
     rem2d_handle* h = new rem2d_handle();
     h->cfg = *cfg;
     h->user_stream = (cudaStream_t)cfg->stream;
-    auto fail = [&](const char* what, cudaError_t err) { g_create_err = std::string(what) + ": " + cudaGetErrorString(err); delete h; return REM2D_E_CUDA; };
+    options_from_env(h->opt);
+    // every failure path releases what was created so far (rem2d_destroy copes with a partially built handle)
+    auto fail = [&](const char* what, cudaError_t err) { g_create_err = std::string(what) + ": " + cudaGetErrorString(err); rem2d_destroy(h); return REM2D_E_CUDA; };
     if ((e = cudaMalloc(&h->d_ter, sizeof(Terrain))) != cudaSuccess) return fail("cudaMalloc terrain", e);
     if ((e = cudaMalloc(&h->d_consts, sizeof(Consts))) != cudaSuccess) return fail("cudaMalloc consts", e);
     if ((e = cudaMalloc(&h->d_counters, sizeof(unsigned long long) * REM2D_N_COUNTERS)) != cudaSuccess) return fail("cudaMalloc counters", e);
-    cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS);
-    Consts k;
-    k.dt = cfg->dt; k.gravity_y = cfg->gravity_y;
-    k.friction = sqrtf(cfg->terrain_friction * cfg->module_friction);       // b2MixFriction
-    k.vel_iters = cfg->velocity_iterations; k.pos_iters = cfg->position_iterations;
-    k.continuous = cfg->continuous; k.allow_sleep = cfg->allow_sleep; k.terminate = cfg->terminate;
-    k.evaluation_steps = cfg->evaluation_steps;
-    k.p_gain = cfg->p_gain; k.wod_speed = cfg->wod_speed; k.env_length = cfg->env_length;
+    if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS)) != cudaSuccess) return fail("cudaMemset counters", e);
+    Consts k = make_consts(cfg);
     if ((e = cudaMemcpy(h->d_consts, &k, sizeof(k), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy consts", e);
     for (auto& c : h->cls) {
         if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
         if ((e = cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-        cudaEventCreate(&c.t_begin); cudaEventCreate(&c.t_end);
+        if ((e = cudaEventCreate(&c.t_begin)) != cudaSuccess || (e = cudaEventCreate(&c.t_end)) != cudaSuccess) return fail("cudaEventCreate", e);
     }
-    cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
-    h->tail_pool.resize(64);
-    for (auto& st : h->tail_pool) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&h->pool_done, cudaEventDisableTiming);
-    cudaMallocHost(&h->h_poll, sizeof(int) * 16);
-    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if ((e = cudaEventCreate(&h->ev_start)) != cudaSuccess || (e = cudaEventCreate(&h->ev_stop)) != cudaSuccess) return fail("cudaEventCreate", e);
+    h->tail_pool.assign(64, nullptr);
+    for (auto& st : h->tail_pool)
+        if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate (tail pool)", e);
+    if ((e = cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate (poll)", e);
+    if ((e = cudaEventCreateWithFlags(&h->pool_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaMallocHost(&h->h_poll, sizeof(int) * 16)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     {
         int carve = cudaSharedmemCarveoutMaxShared, max_hot = 0;
         if (const char* ev = getenv("REM2D_CARVEOUT")) carve = atoi(ev);      // experiment: percent of the unified L1/shared array
-        for (int q = 0; q < N_CLASSES; ++q) max_hot = std::max(max_hot, g_classes(q).hot_words);
+        for (int q = 0; q < N_CLASSES; ++q)
+            for (int gs = 0; gs <= 5; ++gs) max_hot = std::max(max_hot, g_classes(q).hot_bytes(gs));
         if ((e = rem2d_set_kernel_attributes(max_hot, carve)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
     }
     *out = h;
+    return REM2D_OK;
+}
+
+int rem2d_set_option(rem2d_handle* h, const char* name, double value) {
+    if (!h || !name) return REM2D_E_INVALID;
+    if (!set_option(h->opt, name, value)) { h->err = std::string("set_option: unknown option ") + name; return REM2D_E_INVALID; }
     return REM2D_OK;
 }
 
@@ -280,7 +347,12 @@ int rem2d_destroy(rem2d_handle* h) {
     cudaDeviceSynchronize();
     free_population(h);
     release_buffers(h);
-    for (auto& c : h->cls) { if (c.stream) cudaStreamDestroy(c.stream); if (c.done) cudaEventDestroy(c.done); }
+    for (auto& c : h->cls) {
+        if (c.stream) cudaStreamDestroy(c.stream);
+        if (c.done) cudaEventDestroy(c.done);
+        if (c.t_begin) cudaEventDestroy(c.t_begin);
+        if (c.t_end) cudaEventDestroy(c.t_end);
+    }
     for (auto& st : h->tail_pool) if (st) cudaStreamDestroy(st);
     if (h->poll_stream) cudaStreamDestroy(h->poll_stream);
     if (h->pool_done) cudaEventDestroy(h->pool_done);
@@ -288,7 +360,10 @@ int rem2d_destroy(rem2d_handle* h) {
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    cudaFree(h->d_ter); cudaFree(h->d_consts); cudaFree(h->d_counters);
+    if (h->d_ter) cudaFree(h->d_ter);
+    if (h->d_consts) cudaFree(h->d_consts);
+    if (h->d_counters) cudaFree(h->d_counters);
+    cudaGetLastError();
     delete h;
     return REM2D_OK;
 }
@@ -300,21 +375,7 @@ int rem2d_set_terrain(rem2d_handle* h, const double* y, int32_t n, double step) 
     if (!y || n < 2 || n > RB_MAX_EDGES) { h->err = "set_terrain: need 2..200 vertices"; return REM2D_E_INVALID; }
     cudaSetDevice(h->cfg.device);
     Terrain* t = new Terrain();
-    memset(t, 0, sizeof(Terrain));
-    t->n_edges = n - 1;
-    t->step = (float)step;
-    for (int i = 0; i < n - 1; ++i) {
-        // edgeShape vertices: Python doubles -> float32 (Modular2DEnv.py:294-302)
-        float x1 = (float)((double)i * step), y1 = (float)y[i], x2 = (float)((double)(i + 1) * step), y2 = (float)y[i + 1];
-        t->v1x[i] = x1; t->v1y[i] = y1; t->v2x[i] = x2; t->v2y[i] = y2;
-        // b2EdgeShape::ComputeAABB (radius = polygonRadius) + aabbExtension; single float ops, no contraction possible
-        volatile float lox = (x1 < x2 ? x1 : x2), loy = (y1 < y2 ? y1 : y2), hix = (x1 > x2 ? x1 : x2), hiy = (y1 > y2 ? y1 : y2);
-        volatile float a;
-        a = lox - RB_POLY_RADIUS; t->flx[i] = a - RB_AABB_EXT;
-        a = loy - RB_POLY_RADIUS; t->fly[i] = a - RB_AABB_EXT;
-        a = hix + RB_POLY_RADIUS; t->fhx[i] = a + RB_AABB_EXT;
-        a = hiy + RB_POLY_RADIUS; t->fhy[i] = a + RB_AABB_EXT;
-    }
+    fill_terrain(t, y, n, step);
     cudaError_t e = cudaMemcpy(h->d_ter, t, sizeof(Terrain), cudaMemcpyHostToDevice);
     delete t;
     if (e != cudaSuccess) { h->err = std::string("set_terrain: ") + cudaGetErrorString(e); return REM2D_E_CUDA; }
@@ -324,30 +385,6 @@ int rem2d_set_terrain(rem2d_handle* h, const double* y, int32_t n, double step) 
 }
 
 }  // extern "C"
-
-// joint order inside the creature's island: DFS of b2World::Solve from the newest body, each body's joint
-// list newest first. Pure topology, so it is computed once on the host.
-static void island_joint_order(int nb, const int16_t* parent, uint8_t* order) {
-    const int nj = nb - 1;
-    if (nj <= 0) return;
-    char bodyFlag[64] = {0}, jointFlag[64] = {0};      // nb <= 44 (largest capacity class)
-    int stack[64], sp = 0, n = 0;
-    stack[sp++] = nb - 1;
-    bodyFlag[nb - 1] = 1;
-    while (sp > 0) {
-        const int b = stack[--sp];
-        for (int j = nj - 1; j >= 0; --j) {
-            if (parent[j] != b && j + 1 != b) continue;
-            if (jointFlag[j]) continue;
-            const int other = parent[j] == b ? j + 1 : parent[j];
-            order[n++] = (uint8_t)j;
-            jointFlag[j] = 1;
-            if (bodyFlag[other]) continue;
-            stack[sp++] = other;
-            bodyFlag[other] = 1;
-        }
-    }
-}
 
 template <typename T>
 static cudaError_t upload_array(rem2d_handle* h, int slot, const T* src, size_t n, const T** dst) {
@@ -373,8 +410,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
     h->creature_class.assign(n, -1);
     h->creature_lane.assign(n, -1);
     std::vector<std::vector<int>> members(N_CLASSES);
-    int min_class = 0;
-    if (const char* e = getenv("REM2D_MIN_CLASS")) min_class = std::max(0, std::min(N_CLASSES - 1, atoi(e)));   // experiment
+    const int min_class = h->opt.min_class;      // experiment: force small creatures into a larger class
     for (int c = 0; c < n; ++c) {
         int nb = pop->body_off[c + 1] - pop->body_off[c];
         if (nb < 1) { h->err = "upload: creature without a root body"; return REM2D_E_INVALID; }
@@ -439,18 +475,17 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         // (227 KB each) is divided among them in proportion to their work (bodies to simulate); a class never gets more
         // warps than it has batches, and what it cannot use is handed to the others. Without this the largest class
         // would occupy every SM until its last creature dies and the remaining classes would run after it.
-        double smem_kb = 227.0, small_weight = 1.0;
-        if (const char* e = getenv("REM2D_SMALL_WEIGHT")) small_weight = atof(e);    // experiment: share of the small classes
-        if (const char* e = getenv("REM2D_SMEM_BUDGET_KB")) smem_kb = atof(e);       // experiments with a smaller carve-out
+        const double smem_kb = h->opt.smem_budget_kb, small_weight = h->opt.small_weight;
         double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98;
         double work[N_CLASSES], smem[N_CLASSES];
         bool fixed[N_CLASSES];
         for (int k = 0; k < N_CLASSES; ++k) {
-            work[k] = 0.0; fixed[k] = members[k].empty(); smem[k] = g_classes(k).hot_words * 128.0 + 1024.0;
+            work[k] = 0.0; fixed[k] = members[k].empty(); smem[k] = g_classes(k).hot_bytes(class_gs(h, k)) + 1024.0;
             // per-creature cost ~ tick latency of its size: measured ~0.3 ms + 0.085 ms per body for a resident warp; lone
             // bodies fall asleep after landing and cost almost nothing
             for (int c : members[k]) { int nbc = pop->body_off[c + 1] - pop->body_off[c]; work[k] += nbc == 1 ? 1.0 : 3.5 + nbc; }
             if (g_classes(k).nb <= 8) work[k] *= small_weight;
+            work[k] *= (double)(1 << class_gs(h, k));      // warps per resident creature
             h->cls[k].episode_grid = 0;
         }
         // warps_k = W * work_k with W such that sum_k warps_k * smem_k = budget: every class then needs about the same
@@ -463,9 +498,10 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
             bool changed = false;
             for (int k = 0; k < N_CLASSES; ++k) {
                 if (fixed[k]) continue;
-                if ((int)(W * work[k]) >= h->cls[k].n_batches) {        // the class fits entirely: fix it and give the rest back
-                    h->cls[k].episode_grid = h->cls[k].n_batches;
-                    budget -= h->cls[k].n_batches * smem[k];
+                const int per = 32 >> class_gs(h, k), need = (h->cls[k].n_members + per - 1) / per;    // one group per creature
+                if ((int)(W * work[k]) >= need) {        // the class fits entirely: fix it and give the rest back
+                    h->cls[k].episode_grid = need;
+                    budget -= need * smem[k];
                     fixed[k] = true; changed = true;
                 }
             }
@@ -516,7 +552,7 @@ static int launch_reset(rem2d_handle* h) {
     for (int k = N_CLASSES - 1; k >= 0; --k) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
-        g_classes(k).reset(cs.n_batches, cs.stream, cs.d_state, cs.d_lane_creature, h->dpop);
+        g_classes(k).reset(class_gs(h, k), cs.n_batches, cs.stream, cs.d_state, cs.d_lane_creature, h->dpop);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -553,21 +589,20 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
         for (int k = 0; k < N_CLASSES; ++k) {
             if (redo[k].empty()) continue;
             ClassState& cs = h->cls[k];
-            int batches = (int)((redo[k].size() + 31) / 32);
-            int *d_order = nullptr, *d_queue = nullptr;
-            float* d_slots = nullptr;
-            CK(cudaMalloc(&d_order, sizeof(int) * redo[k].size()));
-            CK(cudaMalloc(&d_queue, sizeof(int)));
-            CK(cudaMalloc(&d_slots, (size_t)batches * g_classes(k).words * 32 * sizeof(float)));
+            const int gs = class_gs(h, k), per = 32 >> gs;
+            const int grid = (int)((redo[k].size() + per - 1) / per), batches = (int)((redo[k].size() + 31) / 32);
+            CK(ensure(cs.b_redo_order, sizeof(int) * (redo[k].size() + 1)));
+            CK(ensure(cs.b_redo_slots, (size_t)batches * g_classes(k).words * 32 * sizeof(float)));
+            int* d_order = (int*)cs.b_redo_order.p;
+            int* d_queue = d_order + redo[k].size();
             CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
-            g_classes(k).episode(batches, h->user_stream, d_slots, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter, h->d_consts,
-                                 max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters, ParkPolicy{0, 0, 0, 0, 0, 0, 0.0f, nullptr, nullptr}, nullptr, nullptr, nullptr);
+            g_classes(k).episode(gs, grid, h->user_stream, (float*)cs.b_redo_slots.p, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter,
+                                 h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
+                                 ParkPolicy{0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr);
             h->launches++;
             CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(h->user_stream));
-            cudaFree(d_order); cudaFree(d_queue); cudaFree(d_slots);
-            (void)cs;
+            CK(cudaStreamSynchronize(h->user_stream));      // redo[] (pageable source of the copy) goes out of scope
         }
     }
     return REM2D_OK;
@@ -602,7 +637,7 @@ static int launch_phased(rem2d_handle* h, int max_ticks) {
         if (ticks > max_ticks - cs.done_ticks) ticks = max_ticks - cs.done_ticks;
         cs.done_ticks += ticks;
         int* lc_dst = cs.d_lc_work[cs.lc_next];
-        g_classes(k).step(batches, cs.stream, cs.d_state, ticks, h->d_ter, h->d_consts, h->d_counters);
+        g_classes(k).step(class_gs(h, k), batches, cs.stream, cs.d_state, ticks, h->d_ter, h->d_consts, h->d_counters);
         CK(cudaMemsetAsync(cs.d_n_alive, 0, sizeof(int), cs.stream));
         compact_plan_kernel<<<(cs.cur_lanes + 127) / 128, 128, 0, cs.stream>>>(cs.d_state, cs.lc_cur, cs.cur_lanes, words, max_ticks,
                                                                               h->d_fitness, h->d_ticks, h->d_alive, h->d_status,
@@ -663,23 +698,19 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     // ones leave the longest-lived creatures on the slow path. Drain / late-start parking never paid off. The number of
     // parked creatures per class is bounded (n/16, at most 4 per SM): in an evolved population where most creatures live
     // long, the rest simply stay on their lanes.
-    int park_ticks = 256, park_late = 256, drain_lanes = 0;
-    double late_frac = 1.0, cap_frac = 1.0 / 16.0;
-    {   // Under-filled GPU (every creature of every class has a lane from the start, e.g. 16384 creatures): tail warps find
+    int park_ticks = 256;
+    double cap_frac = 1.0 / 16.0;
+    {   // Under-filled GPU (every creature of every class has a group from the start, e.g. 16384 creatures): tail warps find
         // free SM resources, so parking earlier pays (16384 creatures: 450 -> 413 ms with 160 ticks and a quarter of a class).
         bool single_round = true;
-        for (int k = 0; k < N_CLASSES; ++k)
-            if (h->cls[k].n_batches && h->cls[k].episode_grid < h->cls[k].n_batches) single_round = false;
-        if (single_round) { park_ticks = park_late = 160; cap_frac = 0.25; }
+        for (int k = 0; k < N_CLASSES; ++k) {
+            const int per = 32 >> class_gs(h, k);
+            if (h->cls[k].n_batches && h->cls[k].episode_grid * per < h->cls[k].n_members) single_round = false;
+        }
+        if (single_round) { park_ticks = 160; cap_frac = 0.25; }
     }
-    if (const char* e = getenv("REM2D_PARK_TICKS")) park_ticks = park_late = atoi(e);
-    if (const char* e = getenv("REM2D_PARK_LATE")) park_late = atoi(e);
-    if (const char* e = getenv("REM2D_PARK_LATE_FROM")) late_frac = atof(e);
-    if (const char* e = getenv("REM2D_PARK_CAP")) cap_frac = atof(e);
-    if (const char* e = getenv("REM2D_DRAIN_LANES")) drain_lanes = atoi(e);
-    int lead_from = 0; double lead_ticks = 100.0;
-    if (const char* e = getenv("REM2D_PARK_LEAD_FROM")) lead_from = atoi(e);
-    if (const char* e = getenv("REM2D_PARK_LEAD")) lead_ticks = atof(e);
+    if (h->opt.park_ticks >= 0) park_ticks = h->opt.park_ticks;
+    if (h->opt.park_cap >= 0.0) cap_frac = h->opt.park_cap;
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
     CK(cudaEventRecord(h->ev_start, h->user_stream));
     int rc = fork_streams(h);
@@ -688,18 +719,19 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     // latency and the run takes about one creature lifetime. Measured (tools/small_pop.py, L-system creatures): 2.4x faster
     // than the bulk mode at 128 creatures, 1.9x at 1024, 1.2x at 6144, break-even near 10^4, 0.6x at 16384 (the bulk mode has
     // 32x the lane efficiency).
-    int warp_mode_max = h->n_sms * 48;
-    if (const char* e = getenv("REM2D_WARP_MODE_MAX")) warp_mode_max = atoi(e);
+    const int warp_mode_max = h->opt.warp_mode_max >= 0 ? h->opt.warp_mode_max : h->n_sms * 48;
     const bool warp_mode = h->n_creatures <= warp_mode_max;
     if (warp_mode) park_ticks = 0;
+    const bool trace = h->opt.trace != 0;
     for (int k = N_CLASSES - 1; k >= 0; --k) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
         CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
         CK(cudaEventRecord(cs.t_begin, cs.stream));
-        if (warp_mode) {
-            g_classes(k).warp_mode(cs.n_members, cs.stream, cs.d_state, cs.d_lane_creature, h->dpop, h->d_ter, h->d_consts, max_ticks,
-                                   h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters);
+        if (warp_mode) {      // queue mode with a whole warp per creature and one warp for every creature
+            g_classes(k).episode(5, cs.n_members, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
+                                 h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
+                                 ParkPolicy{0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr);
             CK(cudaEventRecord(cs.t_end, cs.stream));
             h->launches++;
             continue;
@@ -709,10 +741,8 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         ParkPolicy park;
         park.ticks = park_ticks < max_ticks ? park_ticks : 0;
         park.cap = std::min(cs.n_members, std::max(32, std::min((int)(h->n_sms * 64 * cap_frac), (int)(cs.n_members * cap_frac))));
-        park.late_ticks = park_late; park.late_from = (int)(late_frac * cs.n_members); park.drain_lanes = drain_lanes;
-        park.lead_from = lead_from; park.lead = (float)(lead_ticks * h->cfg.wod_speed);
         park.trace = nullptr; park.tail_trace = nullptr;
-        if (getenv("REM2D_TRACE")) {
+        if (trace) {
             const size_t tb = (size_t)std::max(cs.n_members, 1) * 4 * sizeof(unsigned int);
             CK(ensure(cs.b_ttrace, tb));
             CK(cudaMemsetAsync(cs.b_ttrace.p, 0, tb, cs.stream));
@@ -722,8 +752,8 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
             CK(cudaMemsetAsync(cs.b_trace.p, 0, bytes, cs.stream));
             park.trace = (unsigned int*)cs.b_trace.p;
         }
-        g_classes(k).episode(cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
-                             h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
+        g_classes(k).episode(class_gs(h, k), cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop,
+                             h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
                              park, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive);
         CK(cudaMemcpyAsync(cs.h_n_alive, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, cs.stream));
         CK(cudaEventRecord(cs.t_end, cs.stream));
@@ -775,9 +805,9 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
                 if (cnt > launched[k]) ++waited[k]; else waited[k] = 0;
                 if (cnt > launched[k] && (finished_now[k] || cnt - launched[k] >= 4 || waited[k] >= 3)) {
                     waited[k] = 0;
-                    g_classes(k).tail(cnt - launched[k], idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
+                    g_classes(k).tail(h->opt.tail_group_shift, idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
                                       h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                                      getenv("REM2D_TRACE") ? (unsigned int*)cs.b_ttrace.p : nullptr);
+                                      trace ? (unsigned int*)cs.b_ttrace.p : nullptr);
                     CK(cudaGetLastError());
                     h->launches++;
                     launched[k] = cnt;
@@ -848,7 +878,7 @@ int rem2d_step(rem2d_handle* h, int32_t n_ticks) {
     for (int k = N_CLASSES - 1; k >= 0; --k) {        // most expensive class first
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
-        g_classes(k).step(cs.n_batches, cs.stream, cs.d_state, n_ticks, h->d_ter, h->d_consts, h->d_counters);
+        g_classes(k).step(class_gs(h, k), cs.n_batches, cs.stream, cs.d_state, n_ticks, h->d_ter, h->d_consts, h->d_counters);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -885,8 +915,7 @@ int rem2d_run_episodes(rem2d_handle* h, int32_t max_ticks) {
     // Default: persistent kernel with per-lane refill. REM2D_EPISODE_MODE=phased selects tick phases with survivor
     // compaction instead (measured slower at pop 65536: the run is bound by the sequential ticks of the longest-lived
     // large creature, and phases add a launch/sync per 32 ticks to exactly that critical path).
-    const char* mode = getenv("REM2D_EPISODE_MODE");
-    int rc = (mode && !strcmp(mode, "phased")) ? launch_phased(h, max_ticks) : launch_episodes(h, max_ticks);
+    int rc = h->opt.phased ? launch_phased(h, max_ticks) : launch_episodes(h, max_ticks);
     if (rc) return rc;
     CK(cudaEventSynchronize(h->ev_stop));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev_start, h->ev_stop));
@@ -984,6 +1013,31 @@ int rem2d_debug_tail_trace(rem2d_handle* h, int k, unsigned int* out, int64_t ma
     if ((int64_t)words > max_words) words = (size_t)max_words;
     CK(cudaMemcpy(out, cs.b_ttrace.p, words * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     return parked;
+}
+
+int rem2d_read_roots(rem2d_handle* h, float* root_x, double* wod, int32_t* alive) {
+    if (!h) return REM2D_E_INVALID;
+    if (!h->have_pop) { h->err = "read_roots: no population uploaded"; return REM2D_E_INVALID; }
+    if (!h->state_valid) { h->err = "read_roots: per-creature state was consumed by rem2d_run_episodes; call rem2d_reset first"; return REM2D_E_INVALID; }
+    cudaSetDevice(h->cfg.device);
+    const size_t n = (size_t)std::max(h->n_creatures, 1);
+    CK(ensure(h->b_roots, n * (sizeof(double) + sizeof(float) + sizeof(int))));
+    double* d_wod = (double*)h->b_roots.p;
+    float* d_x = (float*)(d_wod + n);
+    int* d_alive = (int*)(d_x + n);
+    for (int k = 0; k < N_CLASSES; ++k) {
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches) continue;
+        const int n_lanes = cs.n_batches * 32;
+        roots_kernel<<<(n_lanes + 127) / 128, 128, 0, h->user_stream>>>(cs.d_state, cs.d_lane_creature, n_lanes, g_classes(k).words, d_x, d_wod, d_alive);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    if (root_x) CK(cudaMemcpyAsync(root_x, d_x, sizeof(float) * h->n_creatures, cudaMemcpyDeviceToHost, h->user_stream));
+    if (wod) CK(cudaMemcpyAsync(wod, d_wod, sizeof(double) * h->n_creatures, cudaMemcpyDeviceToHost, h->user_stream));
+    if (alive) CK(cudaMemcpyAsync(alive, d_alive, sizeof(int) * h->n_creatures, cudaMemcpyDeviceToHost, h->user_stream));
+    CK(cudaStreamSynchronize(h->user_stream));
+    return REM2D_OK;
 }
 
 float rem2d_last_step_ms(rem2d_handle* h) { return h ? h->last_ms : 0.0f; }

@@ -1,8 +1,11 @@
 // rem2d_device.cuh — device code of the batched REM2D step for sm_100a.
 //
-// Mapping: ONE LANE = ONE CREATURE (one Box2D world of the reference), 32 creatures per warp, one warp
-// per CTA. Nothing on this path is a dense contraction, so there are no tensor-core instructions; the
-// per-tick work is a long chain of dependent fp32 operations on ~1 KB of state per creature.
+// Mapping: a GROUP of G = 2^gs LANES = ONE CREATURE (one Box2D world of the reference), 32/G creatures per warp, one warp
+// per CTA; G is a run-time value per launch (1 for the small capacity classes, 2-8 for the large ones, 32 for the
+// latency-oriented warp-per-creature launches). Nothing on this path is a dense contraction, so there are no tensor-core
+// instructions; the per-tick work is a long chain of dependent fp32 operations on ~1-3 KB of state per creature. The lanes of
+// a group share that chain: the 180 velocity iterations run as a STATIC MODULO SCHEDULE of Box2D's sequential-impulse order
+// (see Sim::build_schedule), the per-body / per-joint / per-contact loops of the other phases are strided over the group.
 //
 //  * cold state (poses, sweeps, fat AABBs, contact pool + manifolds, joint definitions, controller state)
 //    lives in HBM in a lane-interleaved block per batch of 32 creatures: word w of lane l is at
@@ -20,7 +23,11 @@
 // Reference call sites (under /root/reference/ModularER_2D): Modular2DEnv.py:607-653 (step),
 // :600-605 (PID), Controller/m_controller.py:17-21, REM2D_main.py:362-377 (episode loop).
 #pragma once
+#ifdef REM2D_EMU
+#include "rem2d_emu_shim.h"      // tests/emu: lanes are host threads (test infrastructure, never a product path)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <float.h>
 
@@ -157,6 +164,7 @@ enum { CF_KEY, CF_TOI, CF_LNX, CF_LNY, CF_LPX, CF_LPY, CF_P0X, CF_P0Y, CF_P0N, C
 #define CK_TOIFLAG 0x08
 #define CK_TYPE_SHIFT 4      // 2 bits: manifold type
 #define CK_COUNT_SHIFT 6     // 2 bits: manifold pointCount
+#define CK_DESTROY_MARK 0x80000000      // top bit of the toiCount byte (toiCount <= 9): contact is to be destroyed (Sim::collide)
 #define MT_CIRCLES 0
 #define MT_FACE_A 1
 #define MT_FACE_B 2
@@ -203,9 +211,10 @@ struct Cnt { unsigned int c[REM2D_N_COUNTERS]; };   // per lane per launch; summ
 struct Layout {
     int nb, nj, nc, nt;                        // bodies, joints, contact-pool slots, hot (shared memory) touching contacts
     int off_joint, off_cont, off_edge, off_spill, words;      // cold block, words per lane (bodies start at S_COUNT)
-    int hoff_joint, hoff_cont, hot_words;                     // hot block, words per lane (bodies start at 0)
-    int thoff_joint, thoff_cont, thot_rows;                   // hot block of the tail mode, rows of 32 words (see Sim)
+    int hot_words;                                            // hot block with one lane per creature, words per lane
 };
+#define RB_SCHED_ROWS 20      // slots per period of the static schedule (shared-memory rows per warp); longer periods fall back
+#define RB_MAX_SKEW 24        // iteration skew bound of a schedule (ring depth of the position-phase end-of-iteration states)
 __host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
     Layout L;
     L.nb = NB; L.nj = NB - 1 > 0 ? NB - 1 : 1; L.nc = NC; L.nt = NT;
@@ -214,31 +223,43 @@ __host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
     L.off_edge = L.off_cont + CF_COUNT * NC;                  // alpha0 of the static edge bodies
     L.off_spill = L.off_edge + RB_MAX_EDGES;                  // touching contacts beyond NT spill to HBM
     L.words = L.off_spill + HC_COUNT * (NC - NT);
-    L.hoff_joint = HB_COUNT * NB;
-    L.hoff_cont = L.hoff_joint + HJ_COUNT * L.nj;
-    L.hot_words = L.hoff_cont + HC_COUNT * NT;
-    L.thoff_joint = HB_COUNT * ((NB + 31) / 32);
-    L.thoff_cont = L.thoff_joint + HJ_COUNT * ((L.nj + 31) / 32);
-    L.thot_rows = L.thoff_cont + HC_COUNT * ((NT + 31) / 32);
+    L.hot_words = HB_COUNT * NB + HJ_COUNT * L.nj + HC_COUNT * NT;
     return L;
 }
+// Hot block of one warp for groups of G = 2^gs lanes per creature: rows of 32 words. Element e of a creature lives in row
+// (section + (e >> gs) * FIELD_COUNT + field), column (group * G + (e & (G-1))). Sections: bodies, joints, hot contacts, then
+// (G > 1 only) one scratch word per body for the scheduler and RB_SCHED_ROWS rows of schedule entries (column = lane).
+struct HotLayout { int hj_off, hc_off, aux_off, sch_off, rows; };
+__host__ __device__ inline HotLayout make_hot_layout(const Layout& L, int gs) {
+    const int G = 1 << gs;
+    const int rb = (L.nb + G - 1) >> gs, rj = (L.nj + G - 1) >> gs, rt = (L.nt + G - 1) >> gs;
+    HotLayout H;
+    H.hj_off = HB_COUNT * rb;
+    H.hc_off = H.hj_off + HJ_COUNT * rj;
+    H.aux_off = H.hc_off + HC_COUNT * rt;
+    H.sch_off = H.aux_off + (gs ? rb : 0);
+    H.rows = H.sch_off + (gs ? RB_SCHED_ROWS : 0);
+    return H;
+}
 
-// Hot (shared memory) block: rows of 32 words, field f of an element at row (section + element_row * FIELD_COUNT + f).
-// Bulk mode (a warp holds 32 creatures): the column is the lane (already added to `h`), element_row = element index, so
-// bank == lane. Tail mode (a whole warp works on ONE creature): the column is the element index modulo 32 and
-// element_row = index / 32, so lanes that work on different elements hit different banks. Field offsets are immediates in
-// both modes and both modes share one code image (`tail` is a run-time flag).
+// One creature. All G lanes of the creature's group hold the same Sim (same cold column `g`, same hot column base `h`) and call
+// every member function TOGETHER; functions marked "leader" are executed by sub == 0 only and everything the other lanes need
+// afterwards is broadcast or read after a group barrier. With G == 1 the code degenerates to the sequential per-lane form.
+// Group barriers use the group's own lane mask, so groups of a warp never wait for each other inside a phase.
 struct Sim {
     Layout L;
-    bool tail;
-    int hj_off, hc_off;       // section rows of the joints / contacts for the current mode
-    int e_shift, e_mask;      // element -> (row, column): (e, 0) in bulk mode, (e >> 5, e & 31) in tail mode
-    float* g;                 // cold block of this batch, already offset by lane
-    float* h;                 // hot block of this warp in shared memory, already offset by lane
+    int gs, G, sub, lead;     // lanes per creature = 1 << gs; my index in the group; absolute lane of the group leader
+    unsigned gmask;           // lanes of my group
+    int hj_off, hc_off, aux_off, sch_off;   // section rows of the hot block for this gs
+    int e_shift, e_mask;      // element -> (row, column): (e >> gs, e & (G-1))
+    float* g;                 // cold block of this batch, already offset by the creature's column
+    float* h;                 // hot block of this warp in shared memory, already offset by the group's first column
     const Terrain* __restrict__ ter;
     const Consts* __restrict__ k;
     Cnt cnt;
     int nb, nj;
+    // schedule of the current tick (group-uniform): period (slots), largest iteration skew; sched_P == 0: sequential fallback
+    int sched_P, sched_smax;
 
     // ---- accessors
     __device__ __forceinline__ float& S(int f) { return g[f * 32]; }
@@ -258,18 +279,34 @@ struct Sim {
     __device__ __forceinline__ int Ci(int f, int c) { return __float_as_int(C(f, c)); }
     __device__ __forceinline__ void setCi(int f, int c, int v) { C(f, c) = __int_as_float(v); }
     __device__ __forceinline__ float& EA(int e) { return g[(L.off_edge + e) * 32]; }
-    __device__ __forceinline__ void set_mode(bool tail_mode) {
-        tail = tail_mode;
-        hj_off = tail ? L.thoff_joint : L.hoff_joint;
-        hc_off = tail ? L.thoff_cont : L.hoff_cont;
-        e_shift = tail ? 5 : 0; e_mask = tail ? 31 : 0;
+    // lane = lane index in the warp; hot = the warp's hot block
+    __device__ __forceinline__ void set_group(int gshift, int lane, float* hot) {
+        gs = gshift; G = 1 << gs; sub = lane & (G - 1); lead = lane & ~(G - 1);
+        gmask = gs == 5 ? 0xffffffffu : (((1u << G) - 1u) << lead);
+        const HotLayout H = make_hot_layout(L, gs);
+        hj_off = H.hj_off; hc_off = H.hc_off; aux_off = H.aux_off; sch_off = H.sch_off;
+        e_shift = gs; e_mask = G - 1;
+        h = hot + lead;
+        sched_P = 0; sched_smax = 0;
     }
+    // ---- group primitives
+    __device__ __forceinline__ void gsync() { __syncwarp(gmask); }
+    __device__ __forceinline__ int bcast(int v) { return gs ? __shfl_sync(gmask, v, lead) : v; }
+    __device__ __forceinline__ bool leader() const { return sub == 0; }
+    __device__ __forceinline__ float group_min(float v) {
+        for (int o = G >> 1; o > 0; o >>= 1) v = min2(v, __shfl_xor_sync(gmask, v, o));
+        return v;
+    }
+    __device__ __forceinline__ bool group_any(bool v) { return gs ? (__ballot_sync(gmask, v) != 0u) : v; }
+    __device__ __forceinline__ bool group_all(bool v) { return gs ? (__ballot_sync(gmask, v) == gmask) : v; }
     __device__ __forceinline__ float* hot_elem(int section, int count, int e) {     // field 0 of element e
         return h + ((section + (e >> e_shift) * count) << 5) + (e & e_mask);
     }
     __device__ __forceinline__ float& HB(int f, int i) { return hot_elem(0, HB_COUNT, i)[f * 32]; }
     __device__ __forceinline__ float& HJ(int f, int j) { return hot_elem(hj_off, HJ_COUNT, j)[f * 32]; }
     __device__ __forceinline__ int HJi(int f, int j) { return __float_as_int(HJ(f, j)); }
+    __device__ __forceinline__ int& AUX(int b) { return *(int*)hot_elem(aux_off, 1, b); }           // scheduler scratch, one word per body
+    __device__ __forceinline__ int& SCH(int p, int lane_in_group) { return *(int*)(h + ((sch_off + p) << 5) + lane_in_group); }
     // Hot contact slot t: shared memory for t < NT, a spill region of the cold block otherwise. The callee gets the
     // address of field 0 and the stride between fields; the two call sites are specialised by the compiler
     // (LDS/STS vs LDG/STG).
@@ -355,17 +392,25 @@ struct Sim {
 
 
     // ---- world construction: b2Body/b2Fixture creation (mass data, sweep, proxy fat AABB), joints, controllers and
-    // episode scalars of creature c (c < 0: empty lane). Mirrors oracle world_build()/body_init().
+    // episode scalars of creature c (c < 0: empty column). Mirrors oracle world_build()/body_init(). Group-cooperative: bodies,
+    // joints and the edge table are strided over the lanes of the group; ends with a group barrier.
     __device__ void build_world(const DevPop& p, int c) {
-        for (int w = 0; w < S_COUNT; ++w) g[w * 32] = 0.0f;
-        if (c < 0) { nb = 0; nj = 0; setSi(S_NB, 0); setSi(S_ALIVE, 0); return; }
+        if (c < 0) {
+            if (leader()) { for (int w = 0; w < S_COUNT; ++w) g[w * 32] = 0.0f; setSi(S_NB, 0); setSi(S_ALIVE, 0); }
+            nb = 0; nj = 0;
+            gsync();
+            return;
+        }
         const int b0 = p.body_off[c], j0 = b0 - c;
         nb = p.body_off[c + 1] - b0; nj = nb - 1;
-        setSi(S_NB, nb); setSi(S_NC, 0); setSi(S_ALIVE, 1); setSi(S_TICKS, 0);
-        setSd(S_WOD_LO, 0.0); setSd(S_FIT_LO, 0.0);
-        S(S_INVDT0) = 0.0f; setSi(S_NEWFIX, 1); setSi(S_STATUS, 0); setSi(S_NADV, 0);
-        for (int e = 0; e < RB_MAX_EDGES; ++e) EA(e) = 0.0f;
-        for (int i = 0; i < nb; ++i) {
+        if (leader()) {
+            for (int w = 0; w < S_COUNT; ++w) g[w * 32] = 0.0f;
+            setSi(S_NB, nb); setSi(S_NC, 0); setSi(S_ALIVE, 1); setSi(S_TICKS, 0);
+            setSd(S_WOD_LO, 0.0); setSd(S_FIT_LO, 0.0);
+            S(S_INVDT0) = 0.0f; setSi(S_NEWFIX, 1); setSi(S_STATUS, 0); setSi(S_NADV, 0);
+        }
+        for (int e = sub; e < RB_MAX_EDGES; e += G) EA(e) = 0.0f;
+        for (int i = sub; i < nb; i += G) {
             const int shape = p.shape[b0 + i];
             const float hx = p.hx[b0 + i], hy = p.hy[b0 + i];
             const float density = 1.0f;
@@ -419,7 +464,7 @@ struct Sim {
             B(BF_FLX, i) = lo.x - RB_AABB_EXT; B(BF_FLY, i) = lo.y - RB_AABB_EXT;
             B(BF_FHX, i) = hi.x + RB_AABB_EXT; B(BF_FHY, i) = hi.y + RB_AABB_EXT;
         }
-        for (int j = 0; j < nj; ++j) {
+        for (int j = sub; j < nj; j += G) {
             setJi(JF_META, j, (int)p.joint_parent[j0 + j] | ((int)p.joint_order[j0 + j] << 8));
             J(JF_LAAX, j) = p.anchor_a[2 * (j0 + j)]; J(JF_LAAY, j) = p.anchor_a[2 * (j0 + j) + 1];
             J(JF_LABX, j) = p.anchor_b[2 * (j0 + j)]; J(JF_LABY, j) = p.anchor_b[2 * (j0 + j) + 1];
@@ -430,6 +475,7 @@ struct Sim {
             setJd(JF_AMP, j, cc[0]); setJd(JF_PHASE, j, cc[1]); setJd(JF_FREQ, j, cc[2]);
             setJd(JF_OFFS, j, cc[3]); setJd(JF_ISTATE, j, cc[4]);
         }
+        gsync();
     }
 
     // ---- contact pool (creation order; index nc-1 is the newest == head of Box2D's lists)
@@ -645,15 +691,27 @@ struct Sim {
         }
     }
 
-    // b2ContactManager::Collide, newest contact first
+    // b2ContactManager::Collide, newest contact first. Group-cooperative: the narrow phase of the pool contacts is strided over
+    // the lanes (descending, so that G == 1 keeps Box2D's order exactly); contacts whose fat AABBs stopped overlapping are only
+    // MARKED and then removed by the leader, newest first. This is the sequential result: a contact is looked at only if its
+    // body is awake, and neither b2Contact::Update nor the destruction can change the awake flag of an awake body, so no
+    // contact's treatment depends on what happened to another contact of the same pass.
     __device__ void collide() {
-        for (int i = Si(S_NC) - 1; i >= 0; --i) {
+        const int nc = bcast(Si(S_NC));
+        bool marked = false;
+        for (int i = nc - 1 - sub; i >= 0; i -= G) {
             int key = Ci(CF_KEY, i);
             int b = key_body(key);
             if (!(Bi(BF_FLAGS, b) & BFL_AWAKE)) continue;
-            if (!overlap_edge(key_edge(key), b)) { destroy_contact(i); continue; }
+            if (!overlap_edge(key_edge(key), b)) { setCi(CF_KEY, i, key | CK_DESTROY_MARK); marked = true; continue; }
             contact_update(i);
         }
+        if (group_any(marked)) {          // (group_any is a group barrier as well)
+            if (leader())
+                for (int i = nc - 1; i >= 0; --i)
+                    if (Ci(CF_KEY, i) & CK_DESTROY_MARK) destroy_contact(i);
+        }
+        gsync();
     }
 
     // ---- contact constraints in shared memory
@@ -963,18 +1021,18 @@ struct Sim {
     }
 
     // ---- b2World::Solve for the creature's single island (+ SynchronizeFixtures + FindNewContacts)
-    // solve_pre: integrate velocities, stage + warm start the constraints; returns false if the island sleeps.
-    // solve_velocity: the 180 sequential-impulse iterations. solve_post: store impulses, integrate positions, position
-    // iterations, sleeping, SynchronizeFixtures + FindNewContacts.
+    // solve_pre: integrate velocities, stage + warm start the constraints, build the schedule; returns false if the island
+    // sleeps. solve_velocity: the 180 sequential-impulse iterations. solve_post: store impulses, integrate positions, position
+    // iterations, sleeping, SynchronizeFixtures + FindNewContacts. All group-cooperative (every lane of the group calls them).
     __device__ bool solve_pre(float dtRatio, int& nt_out) {
         const float hdt = k->dt;
         nt_out = 0;
         // a creature is one island (tree of joints); it is solved iff its seed body is awake. Jointed
         // creatures are always awake here (the motor-speed setter woke them); a lone body may sleep.
         bool anyAwake = false;
-        for (int b = 0; b < nb; ++b) anyAwake |= (Bi(BF_FLAGS, b) & BFL_AWAKE) != 0;
-        if (!anyAwake) return false;
-        for (int b = 0; b < nb; ++b) {
+        for (int b = sub; b < nb; b += G) anyAwake |= (Bi(BF_FLAGS, b) & BFL_AWAKE) != 0;
+        if (!group_any(anyAwake)) return false;
+        for (int b = sub; b < nb; b += G) {
             set_awake(b, true);
             float cx = B(BF_CX, b), cy = B(BF_CY, b), a = B(BF_A, b);
             B(BF_C0X, b) = cx; B(BF_C0Y, b) = cy; B(BF_A0, b) = a;
@@ -990,44 +1048,34 @@ struct Sim {
             cnt.c[REM2D_CNT_BODY_TICKS]++;
         }
         // contact constraints: touching contacts, newest first (per-body list order is what matters:
-        // contacts of different bodies only share the static terrain and commute exactly)
-        int nc = Si(S_NC), nt = 0;
-        for (int c = nc - 1; c >= 0; --c) {
-            int key = Ci(CF_KEY, c);
-            int fl = key_flags(key);
-            if (!(fl & CK_ENABLED) || !(fl & CK_TOUCHING)) continue;
-            int b = key_body(key);
-            with_contact(nt, [&](float* hc, const int st) {
+        // contacts of different bodies only share the static terrain and commute exactly). The leader lists them (slot t
+        // remembers its pool index), the group builds the constraints.
+        int nt = 0;
+        if (leader()) {
+            const int nc = Si(S_NC);
+            for (int c = nc - 1; c >= 0; --c) {
+                int fl = key_flags(Ci(CF_KEY, c));
+                if (!(fl & CK_ENABLED) || !(fl & CK_TOUCHING)) continue;
+                with_contact(nt, [&](float* hc, const int st) { hc[HC_META * st] = __int_as_float(c); });
+                ++nt;
+            }
+        }
+        nt = bcast(nt);
+        gsync();
+        for (int t = sub; t < nt; t += G)
+            with_contact(t, [&](float* hc, const int st) {
+                const int c = __float_as_int(hc[HC_META * st]);
+                const int b = key_body(Ci(CF_KEY, c));
                 contact_init_velocity(hc, st, c, mk(B(BF_CX, b), B(BF_CY, b)), B(BF_A, b), B(BF_INVM, b), B(BF_INVI, b), dtRatio, true);
             });
-            ++nt;
-        }
-        // warm start contacts
-        for_contacts(nt, [&](float* hc, const int st, int) {
-            int meta = __float_as_int(hc[HC_META * st]);
-            int b = meta & 0xff, count = (meta >> 8) & 3;
-            float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
-            V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
-            V2 normal = mk(hc[HC_NX * st], hc[HC_NY * st]), tangent = cross_vs(normal, 1.0f);
-            {
-                V2 r = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
-                V2 P = hc[HC_NI0 * st] * normal + hc[HC_TI0 * st] * tangent;
-                wB += iB * cross(r, P); vB = vB + mB * P;
-            }
-            if (count > 1) {
-                V2 r = mk(hc[HC_R1X * st], hc[HC_R1Y * st]);
-                V2 P = hc[HC_NI1 * st] * normal + hc[HC_TI1 * st] * tangent;
-                wB += iB * cross(r, P); vB = vB + mB * P;
-            }
-            HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
-        });
-        // joints: InitVelocityConstraints in island order (slot s = s-th joint of the island)
-        for (int s = 0; s < nj; ++s) {
+        // joints: InitVelocityConstraints in island order (slot s = s-th joint of the island); the warm-start impulses are
+        // scaled and stored here and APPLIED below in Box2D's order
+        for (int s = sub; s < nj; s += G) {
             int jm = Ji(JF_META, s);
             int j = (jm >> 8) & 0xff;                  // joint index solved s-th
             int a = Ji(JF_META, j) & 0xff, b = j + 1;
             float aA = B(BF_A, a), aB = B(BF_A, b);
-            float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+            float mA = B(BF_INVM, a), iA = B(BF_INVI, a), mB = B(BF_INVM, b), iB = B(BF_INVI, b);
             Rot qA = rot_set(aA), qB = rot_set(aB);
             V2 rA = rmul(qA, mk(J(JF_LAAX, j), J(JF_LAAY, j)) - mk(0.0f, 0.0f));
             V2 rB = rmul(qB, mk(J(JF_LABX, j), J(JF_LABY, j)) - mk(0.0f, 0.0f));
@@ -1048,13 +1096,6 @@ struct Sim {
             else { limit = 0; impz = 0.0f; }
             setJi(JF_LIMIT, j, limit);
             impx *= dtRatio; impy *= dtRatio; impz *= dtRatio; mimp *= dtRatio;
-            V2 vA = mk(HB(HB_VX, a), HB(HB_VY, a)); float wA = HB(HB_W, a);
-            V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
-            V2 P = mk(impx, impy);
-            vA = vA - mA * P; wA -= iA * (cross(rA, P) + mimp + impz);
-            vB = vB + mB * P; wB += iB * (cross(rB, P) + mimp + impz);
-            HB(HB_VX, a) = vA.x; HB(HB_VY, a) = vA.y; HB(HB_W, a) = wA;
-            HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
             HJ(HJ_META, s) = __int_as_float(a | (b << 8) | (limit << 16) | (j << 24));
             HJ(HJ_RAX, s) = rA.x; HJ(HJ_RAY, s) = rA.y; HJ(HJ_RBX, s) = rB.x; HJ(HJ_RBY, s) = rB.y;
             HJ(HJ_EXX, s) = exx; HJ(HJ_EYX, s) = eyx; HJ(HJ_EYY, s) = eyy;
@@ -1071,37 +1112,217 @@ struct Sim {
             HJ(HJ_MSPEED, s) = J(JF_MSPEED, j);
             HJ(HJ_MAXIMP, s) = hdt * J(JF_MAXT, j);
         }
+        gsync();
+        // warm start in Box2D's order: all contacts (b2ContactSolver::WarmStart), then the joints in island order. The
+        // additions to a body's velocity do not commute in float arithmetic, so the leader applies them one after the other.
+        if (leader()) {
+            for_contacts(nt, [&](float* hc, const int st, int) {
+                int meta = __float_as_int(hc[HC_META * st]);
+                int b = meta & 0xff, count = (meta >> 8) & 3;
+                float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+                V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
+                V2 normal = mk(hc[HC_NX * st], hc[HC_NY * st]), tangent = cross_vs(normal, 1.0f);
+                {
+                    V2 r = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
+                    V2 P = hc[HC_NI0 * st] * normal + hc[HC_TI0 * st] * tangent;
+                    wB += iB * cross(r, P); vB = vB + mB * P;
+                }
+                if (count > 1) {
+                    V2 r = mk(hc[HC_R1X * st], hc[HC_R1Y * st]);
+                    V2 P = hc[HC_NI1 * st] * normal + hc[HC_TI1 * st] * tangent;
+                    wB += iB * cross(r, P); vB = vB + mB * P;
+                }
+                HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+            });
+            for (int s = 0; s < nj; ++s) {
+                const int meta = HJi(HJ_META, s);
+                const int a = meta & 0xff, b = (meta >> 8) & 0xff;
+                const float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+                const V2 rA = mk(HJ(HJ_RAX, s), HJ(HJ_RAY, s)), rB = mk(HJ(HJ_RBX, s), HJ(HJ_RBY, s));
+                const float impz = HJ(HJ_IMPZ, s), mimp = HJ(HJ_MIMP, s);
+                V2 vA = mk(HB(HB_VX, a), HB(HB_VY, a)); float wA = HB(HB_W, a);
+                V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
+                V2 P = mk(HJ(HJ_IMPX, s), HJ(HJ_IMPY, s));
+                vA = vA - mA * P; wA -= iA * (cross(rA, P) + mimp + impz);
+                vB = vB + mB * P; wB += iB * (cross(rB, P) + mimp + impz);
+                HB(HB_VX, a) = vA.x; HB(HB_VY, a) = vA.y; HB(HB_W, a) = wA;
+                HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+            }
+        }
         nt_out = nt;
+        build_schedule(nt, false);
         return true;
     }
+    // ---------------- static modulo schedule of one sequential-impulse sweep
+    // Box2D solves the constraints of an island one after the other, every iteration in the same order (velocity: joints in
+    // island order, then contacts; position: contacts, then joints). Two constraints commute EXACTLY iff they share no body,
+    // so the order only matters per body: each body sees its incident constraints in sequence order, iteration after
+    // iteration. The schedule gives constraint c a time tau_c = skew_c * P + slot_c such that, for every body, the times of its
+    // incident constraints increase in sequence order and span less than one period P: iteration `it` of c then runs at time
+    // (it + skew_c) * P + slot_c, every body still sees exactly Box2D's order (bit-identical results), at most G constraints
+    // share a slot (one per lane), and in steady state every lane solves one constraint per slot - consecutive iterations
+    // are software-pipelined across the creature's joint tree. Built greedily in sequence order (each constraint at the
+    // earliest slot after its bodies' previous constraints that has a free lane), the period is tried upwards from the lower
+    // bound max(ceil(n/G), max body degree); measured on L-system creatures: the achieved period IS that bound for 97 % of
+    // them (tests/emu + tools/sched_sim.py). The run is then fully static: at slot p of super-step T lane l executes entry
+    // SCH(p, l) for iteration T - skew - no readiness checks, one group barrier per slot.
+    // Entry: bit 31 valid | bit 30 contact | skew << 8 | index (joint slot s or hot contact slot t).
+    // Times are packed as (skew << 5 | slot); AUX(b) = deg | rem << 6 | first << 12 | last << 22 (10-bit times, 0x3ff = none).
+    #define SCH_VALID 0x80000000
+    #define SCH_CONTACT 0x40000000
+    __device__ __forceinline__ int sched_body_b(bool contact, int idx) {
+        if (contact) return __float_as_int(hot_elem(hc_off, HC_COUNT, idx)[HC_META * 32]) & 0xff;
+        return (HJi(HJ_META, idx) >> 8) & 0xff;
+    }
+    __device__ bool try_schedule(int n, int nt, bool position_order, int P, int& smax_out) {      // leader
+        int smax = 0;
+        for (int q = 0; q < n; ++q) {
+            // q-th constraint of the sweep
+            bool contact; int idx;
+            if (position_order) { contact = q < nt; idx = contact ? q : q - nt; }
+            else { contact = q >= nj; idx = contact ? q - nj : q; }
+            const int ub = sched_body_b(contact, idx);
+            const int ua = contact ? -1 : (HJi(HJ_META, idx) & 0xff);
+            int lo = 0, hi = 0x7fffffff;
+            const int wb = AUX(ub);
+            const int wa = ua >= 0 ? AUX(ua) : 0;
+            {
+                const int first = (wb >> 12) & 0x3ff, last = (wb >> 22) & 0x3ff, rem = (wb >> 6) & 0x3f;
+                if (first != 0x3ff) {
+                    int t = last + 1; if ((t & 31) == P) t = (t & ~31) + 32;
+                    lo = t;
+                    int pp = (first & 31) + (P - rem), ss = first >> 5;
+                    if (pp >= P) { pp -= P; ++ss; }
+                    hi = (ss << 5) | pp;
+                }
+            }
+            if (ua >= 0) {
+                const int first = (wa >> 12) & 0x3ff, last = (wa >> 22) & 0x3ff, rem = (wa >> 6) & 0x3f;
+                if (first != 0x3ff) {
+                    int t = last + 1; if ((t & 31) == P) t = (t & ~31) + 32;
+                    if (t > lo) lo = t;
+                    int pp = (first & 31) + (P - rem), ss = first >> 5;
+                    if (pp >= P) { pp -= P; ++ss; }
+                    const int h2 = (ss << 5) | pp;
+                    if (h2 < hi) hi = h2;
+                }
+            }
+            int t = lo, lane_k = -1;
+            while (t <= hi) {
+                const int pslot = t & 31;
+                for (int kk = 0; kk < G; ++kk)
+                    if (SCH(pslot, kk) == 0) { lane_k = kk; break; }
+                if (lane_k >= 0) break;
+                ++t; if ((t & 31) == P) t = (t & ~31) + 32;
+            }
+            if (lane_k < 0) return false;
+            const int skew = t >> 5;
+            if (skew > RB_MAX_SKEW) return false;
+            if (skew > smax) smax = skew;
+            SCH(t & 31, lane_k) = (int)(SCH_VALID | (contact ? SCH_CONTACT : 0u) | (unsigned)(skew << 8) | (unsigned)idx);
+            {
+                int w = AUX(ub);
+                if (((w >> 12) & 0x3ff) == 0x3ff) w = (w & ~(0x3ff << 12)) | (t << 12);
+                w = (w & ~(0x3ff << 22)) | (t << 22);
+                w -= 1 << 6;
+                AUX(ub) = w;
+            }
+            if (ua >= 0) {
+                int w = AUX(ua);
+                if (((w >> 12) & 0x3ff) == 0x3ff) w = (w & ~(0x3ff << 12)) | (t << 12);
+                w = (w & ~(0x3ff << 22)) | (t << 22);
+                w -= 1 << 6;
+                AUX(ua) = w;
+            }
+        }
+        smax_out = smax;
+        return true;
+    }
+    // Builds the schedule of this tick's velocity sweep (position_order = false; needs the staged HJ_META / HC_META) or
+    // position sweep (true; needs the overlaid PJ_META / PC_META, same low bits). Sets sched_P (0: no schedule, the leader
+    // runs the sweep sequentially) and sched_smax. Group-cooperative; ends with a group barrier.
+    __device__ void build_schedule(int nt, bool position_order) {
+        sched_P = 0; sched_smax = 0;
+        if (gs == 0) return;
+        const int n = nj + nt;
+        if (nt > L.nt || n == 0) { gsync(); return; }      // spilled contacts (rare): sequential sweep
+        // degrees
+        for (int b = sub; b < nb; b += G) AUX(b) = 0;
+        gsync();
+        int P = 0;
+        if (leader()) {
+            for (int s = 0; s < nj; ++s) { const int m = HJi(HJ_META, s); AUX(m & 0xff) += 1; AUX((m >> 8) & 0xff) += 1; }
+            for (int t = 0; t < nt; ++t) AUX(sched_body_b(true, t)) += 1;
+            int maxdeg = 1;
+            for (int b = 0; b < nb; ++b) { const int d = AUX(b); if (d > maxdeg) maxdeg = d; }
+            P = (n + G - 1) >> gs;
+            if (maxdeg > P) P = maxdeg;
+        }
+        P = bcast(P);
+        for (;;) {
+            if (P > RB_SCHED_ROWS) { P = 0; break; }
+            for (int q = 0; q < P; ++q) SCH(q, sub) = 0;
+            for (int b = sub; b < nb; b += G) { const int d = AUX(b) & 0x3f; AUX(b) = d | (d << 6) | (0x3ff << 12) | (0x3ff << 22); }
+            gsync();
+            int ok = 0, smax = 0;
+            if (leader()) ok = try_schedule(n, nt, position_order, P, smax) ? 1 : 0;
+            ok = bcast(ok);
+            if (ok) { sched_smax = bcast(smax); break; }
+            ++P;
+        }
+        sched_P = P;
+        gsync();
+    }
+
     // ---------------- velocity iterations: the hot loop (everything in shared memory)
     // NB: equal limits (|upper-lower| < 2*angularSlop) do not occur: limits are -+pi/2 (module_utility.py:28-29)
     __device__ void solve_velocity(int nt) {
         const int vit = k->vel_iters;
-        for (int it = 0; it < vit; ++it) {
-            for (int s = 0; s < nj; ++s) joint_solve_velocity(s);
-            for_contacts(nt, [&](float* hc, const int st, int) { contact_solve_velocity(hc, st); });
+        if (sched_P) {
+            const int P = sched_P, total = (vit + sched_smax) * P;
+            int pslot = 0, T = 0;
+            for (int q = 0; q < total; ++q) {
+                const int e = SCH(pslot, sub);
+                const int it = T - ((e >> 8) & 0xff);
+                const bool act = e < 0 && it >= 0 && it < vit;
+                if (act && !(e & SCH_CONTACT)) joint_solve_velocity(e & 0xff);
+                if (act && (e & SCH_CONTACT)) contact_solve_velocity(hot_elem(hc_off, HC_COUNT, e & 0xff), 32);
+                gsync();
+                if (++pslot == P) { pslot = 0; ++T; }
+            }
+            return;
         }
+        if (leader())
+            for (int it = 0; it < vit; ++it) {
+                for (int s = 0; s < nj; ++s) joint_solve_velocity(s);
+                for_contacts(nt, [&](float* hc, const int st, int) { contact_solve_velocity(hc, st); });
+            }
+        gsync();
     }
     __device__ void solve_post(int nt) {
         const float hdt = k->dt;
         const int vit = k->vel_iters;
-        cnt.c[REM2D_CNT_JOINT_VSOLVES] += (unsigned)(vit * nj);
-        count_contact_solves(nt, vit);
+        if (leader()) cnt.c[REM2D_CNT_JOINT_VSOLVES] += (unsigned)(vit * nj);
         // store impulses
-        for_contacts(nt, [&](float* hc, const int st, int) {
-            int meta = __float_as_int(hc[HC_META * st]);
-            int c = (meta >> 16) & 0xffff, count = (meta >> 8) & 3;
-            C(CF_P0N, c) = hc[HC_NI0 * st]; C(CF_P0T, c) = hc[HC_TI0 * st];
-            if (count > 1) { C(CF_P1N, c) = hc[HC_NI1 * st]; C(CF_P1T, c) = hc[HC_TI1 * st]; }
-        });
-        for (int s = 0; s < nj; ++s) {
+        for (int t = sub; t < nt; t += G)
+            with_contact(t, [&](float* hc, const int st) {
+                int meta = __float_as_int(hc[HC_META * st]);
+                int c = (meta >> 16) & 0xffff, count = (meta >> 8) & 3;
+                cnt.c[count == 1 ? REM2D_CNT_P1_VSOLVES : REM2D_CNT_M2_VSOLVES] += (unsigned)vit;
+                C(CF_P0N, c) = hc[HC_NI0 * st]; C(CF_P0T, c) = hc[HC_TI0 * st];
+                if (count > 1) { C(CF_P1N, c) = hc[HC_NI1 * st]; C(CF_P1T, c) = hc[HC_TI1 * st]; }
+                contact_init_position(hc, st, c);          // position constraints overlay the hot contact slot
+            });
+        for (int s = sub; s < nj; s += G) {
             int j = (HJi(HJ_META, s) >> 24) & 0xff;
             J(JF_IMPX, j) = HJ(HJ_IMPX, s); J(JF_IMPY, j) = HJ(HJ_IMPY, s); J(JF_IMPZ, j) = HJ(HJ_IMPZ, s);
             J(JF_MIMP, j) = HJ(HJ_MIMP, s);
+            HJ(PJ_LAAX, s) = J(JF_LAAX, j); HJ(PJ_LAAY, s) = J(JF_LAAY, j);      // position overlay of the hot joint slot
+            HJ(PJ_LABX, s) = J(JF_LABX, j); HJ(PJ_LABY, s) = J(JF_LABY, j);
+            HJ(PJ_LOWER, s) = J(JF_LOWER, j); HJ(PJ_UPPER, s) = J(JF_UPPER, j);
         }
         // integrate positions; velocities go back to the cold block, the hot body slots become (c, a)
-        for (int b = 0; b < nb; ++b) {
+        for (int b = sub; b < nb; b += G) {
             V2 c = mk(B(BF_CX, b), B(BF_CY, b)); float a = B(BF_A, b);
             V2 v = mk(HB(HB_VX, b), HB(HB_VY, b)); float w = HB(HB_W, b);
             V2 translation = hdt * v;
@@ -1118,32 +1339,25 @@ struct Sim {
             B(BF_VX, b) = v.x; B(BF_VY, b) = v.y; B(BF_W, b) = w;
             HB(HB_VX, b) = c.x; HB(HB_VY, b) = c.y; HB(HB_W, b) = a;
         }
-        // position constraints: overlay the hot joint / contact slots
-        for (int s = 0; s < nj; ++s) {
-            int meta = HJi(HJ_META, s);
-            int j = (meta >> 24) & 0xff;
-            HJ(PJ_LAAX, s) = J(JF_LAAX, j); HJ(PJ_LAAY, s) = J(JF_LAAY, j);
-            HJ(PJ_LABX, s) = J(JF_LABX, j); HJ(PJ_LABY, s) = J(JF_LABY, j);
-            HJ(PJ_LOWER, s) = J(JF_LOWER, j); HJ(PJ_UPPER, s) = J(JF_UPPER, j);
+        gsync();
+        int positionSolved = 0;
+        if (leader()) {
+            const int pit = k->pos_iters;
+            for (int it = 0; it < pit; ++it) {
+                float minSep = 0.0f;
+                for_contacts(nt, [&](float* hc, const int st, int) { minSep = contact_solve_position(hc, st, RB_BAUMGARTE, minSep); });
+                bool contactsOkay = minSep >= -3.0f * RB_LINEAR_SLOP;
+                bool jointsOkay = true;
+                for (int s = 0; s < nj; ++s) { bool ok = joint_solve_position(s); jointsOkay = jointsOkay && ok; }
+                cnt.c[REM2D_CNT_JOINT_PSOLVES] += (unsigned)nj;
+                if (contactsOkay && jointsOkay) { positionSolved = 1; break; }
+            }
         }
-        for_contacts(nt, [&](float* hc, const int st, int) {
-            int c = (__float_as_int(hc[HC_META * st]) >> 16) & 0xffff;
-            contact_init_position(hc, st, c);
-        });
-        bool positionSolved = false;
-        const int pit = k->pos_iters;
-        for (int it = 0; it < pit; ++it) {
-            float minSep = 0.0f;
-            for_contacts(nt, [&](float* hc, const int st, int) { minSep = contact_solve_position(hc, st, RB_BAUMGARTE, minSep); });
-            bool contactsOkay = minSep >= -3.0f * RB_LINEAR_SLOP;
-            bool jointsOkay = true;
-            for (int s = 0; s < nj; ++s) { bool ok = joint_solve_position(s); jointsOkay = jointsOkay && ok; }
-            cnt.c[REM2D_CNT_JOINT_PSOLVES] += (unsigned)nj;
-            if (contactsOkay && jointsOkay) { positionSolved = true; break; }
-        }
+        positionSolved = bcast(positionSolved);
+        gsync();
         // copy back, synchronize transforms, sleep management
         float minSleepTime = RB_MAXF;
-        for (int b = 0; b < nb; ++b) {
+        for (int b = sub; b < nb; b += G) {
             B(BF_CX, b) = HB(HB_VX, b); B(BF_CY, b) = HB(HB_VY, b); B(BF_A, b) = HB(HB_W, b);
             sync_transform(b);
             if (k->allow_sleep) {
@@ -1156,10 +1370,13 @@ struct Sim {
                 }
             }
         }
+        if (gs) minSleepTime = group_min(minSleepTime);
         if (k->allow_sleep && minSleepTime >= RB_TIME_TO_SLEEP && positionSolved)
-            for (int b = 0; b < nb; ++b) set_awake(b, false);
-        for (int b = nb - 1; b >= 0; --b) synchronize_fixtures(b);
-        find_new_contacts();
+            for (int b = sub; b < nb; b += G) set_awake(b, false);
+        for (int b = sub; b < nb; b += G) synchronize_fixtures(b);      // (independent per body: any order)
+        gsync();
+        if (leader()) find_new_contacts();
+        gsync();
     }
 
     // ---- continuous collision: b2TimeOfImpact / b2Distance with proxy A = terrain edge (identity frame)
@@ -1387,24 +1604,69 @@ struct Sim {
         setSi(S_NADV, n + 1);
     }
 
-    // b2World::SolveTOI
+    // time of impact of pool contact c against its body's sweep (the body of b2World::SolveTOI's inner loop); leaves the
+    // sweeps untouched when both alpha0 are equal (always the case in the first scan of a step)
+    __device__ float contact_toi(int c, int key) {
+        int b = key_body(key), e = key_edge(key);
+        float aA0 = EA(e), aB0 = B(BF_ALPHA0, b);
+        float alpha0 = aA0;
+        Sweep sw;
+        sw.c0 = mk(B(BF_C0X, b), B(BF_C0Y, b)); sw.c = mk(B(BF_CX, b), B(BF_CY, b));
+        sw.a0 = B(BF_A0, b); sw.a = B(BF_A, b); sw.alpha0 = aB0;
+        if (aA0 < aB0) { alpha0 = aB0; set_edge_alpha(e, alpha0); }
+        else if (aB0 < aA0) {
+            alpha0 = aA0;
+            float beta = (alpha0 - sw.alpha0) / (1.0f - sw.alpha0);
+            sw.c0 = sw.c0 + beta * (sw.c - sw.c0);
+            sw.a0 += beta * (sw.a - sw.a0);
+            sw.alpha0 = alpha0;
+            B(BF_C0X, b) = sw.c0.x; B(BF_C0Y, b) = sw.c0.y; B(BF_A0, b) = sw.a0; B(BF_ALPHA0, b) = alpha0;
+        }
+        V2 ev[2] = { mk(__ldg(&ter->v1x[e]), __ldg(&ter->v1y[e])), mk(__ldg(&ter->v2x[e]), __ldg(&ter->v2y[e])) };
+        Prox pb;
+        float hx = B(BF_HX, b), hy = B(BF_HY, b);
+        if (Bi(BF_FLAGS, b) & BFL_CIRCLE) { pb.count = 1; pb.radius = hx; pb.v[0] = mk(0.0f, 0.0f); pb.v[1] = pb.v[2] = pb.v[3] = pb.v[0]; }
+        else { pb.count = 4; pb.radius = RB_POLY_RADIUS; pb.v[0] = mk(-hx, -hy); pb.v[1] = mk(hx, -hy); pb.v[2] = mk(hx, hy); pb.v[3] = mk(-hx, hy); }
+        float t;
+        bool touching = time_of_impact(ev, pb, sw, t);
+        float alpha = 1.0f;
+        if (touching) alpha = min2(alpha0 + (1.0f - alpha0) * t, 1.0f);
+        return alpha;
+    }
+
+    // b2World::SolveTOI. Group-cooperative: the first scan over the contacts - one time-of-impact query per contact of an awake
+    // body, every sweep still at alpha0 = 0, so the queries are independent - is strided over the lanes and leaves its results
+    // in the pool (toi + toiFlag) exactly as Box2D caches them; the leader then runs Box2D's loop, which finds the cached
+    // values, and handles TOI events (rare: 2 % of the ticks) sequentially.
     __device__ void solve_toi() {
         const float dt = k->dt;
-        for (int b = 0; b < nb; ++b) { setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) & ~BFL_ISLAND); B(BF_ALPHA0, b) = 0.0f; }
-        {   // alpha0 of the static edge bodies: clear what the previous step dirtied
+        for (int b = sub; b < nb; b += G) { setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) & ~BFL_ISLAND); B(BF_ALPHA0, b) = 0.0f; }
+        if (leader()) {   // alpha0 of the static edge bodies: clear what the previous step dirtied
             int n = Si(S_NADV);
             if (n > 8) { for (int e = 0; e < RB_MAX_EDGES; ++e) EA(e) = 0.0f; }
             else for (int i = 0; i < n; ++i) EA(Si(S_ADV0 + i)) = 0.0f;
             setSi(S_NADV, 0);
         }
-        int nc = Si(S_NC);
-        for (int c = 0; c < nc; ++c) {
+        int nc = bcast(Si(S_NC));
+        gsync();
+        for (int c = nc - 1 - sub; c >= 0; c -= G) {
             int key = Ci(CF_KEY, c);
             key &= ~((CK_TOIFLAG | CK_ISLAND) << 16);
             key &= 0x00ffffff;                                    // toiCount = 0
+            float alpha = 1.0f;
+            if ((key_flags(key) & CK_ENABLED) && (Bi(BF_FLAGS, key_body(key)) & BFL_AWAKE)) {
+                alpha = contact_toi(c, key);
+                key |= CK_TOIFLAG << 16;
+            }
             setCi(CF_KEY, c, key);
-            C(CF_TOI, c) = 1.0f;
+            C(CF_TOI, c) = alpha;
         }
+        gsync();
+        if (leader()) solve_toi_events(dt);
+        gsync();
+    }
+    __device__ void solve_toi_events(const float dt) {       // leader
+        int nc;
         for (;;) {
             nc = Si(S_NC);
             int minContact = -1; float minAlpha = 1.0f;
@@ -1416,30 +1678,8 @@ struct Sim {
                 float alpha = 1.0f;
                 if (fl & CK_TOIFLAG) alpha = C(CF_TOI, c);
                 else {
-                    int b = key_body(key), e = key_edge(key);
-                    if (!(Bi(BF_FLAGS, b) & BFL_AWAKE)) continue;
-                    float aA0 = EA(e), aB0 = B(BF_ALPHA0, b);
-                    float alpha0 = aA0;
-                    Sweep sw;
-                    sw.c0 = mk(B(BF_C0X, b), B(BF_C0Y, b)); sw.c = mk(B(BF_CX, b), B(BF_CY, b));
-                    sw.a0 = B(BF_A0, b); sw.a = B(BF_A, b); sw.alpha0 = aB0;
-                    if (aA0 < aB0) { alpha0 = aB0; set_edge_alpha(e, alpha0); }
-                    else if (aB0 < aA0) {
-                        alpha0 = aA0;
-                        float beta = (alpha0 - sw.alpha0) / (1.0f - sw.alpha0);
-                        sw.c0 = sw.c0 + beta * (sw.c - sw.c0);
-                        sw.a0 += beta * (sw.a - sw.a0);
-                        sw.alpha0 = alpha0;
-                        B(BF_C0X, b) = sw.c0.x; B(BF_C0Y, b) = sw.c0.y; B(BF_A0, b) = sw.a0; B(BF_ALPHA0, b) = alpha0;
-                    }
-                    V2 ev[2] = { mk(__ldg(&ter->v1x[e]), __ldg(&ter->v1y[e])), mk(__ldg(&ter->v2x[e]), __ldg(&ter->v2y[e])) };
-                    Prox pb;
-                    float hx = B(BF_HX, b), hy = B(BF_HY, b);
-                    if (Bi(BF_FLAGS, b) & BFL_CIRCLE) { pb.count = 1; pb.radius = hx; pb.v[0] = mk(0.0f, 0.0f); pb.v[1] = pb.v[2] = pb.v[3] = pb.v[0]; }
-                    else { pb.count = 4; pb.radius = RB_POLY_RADIUS; pb.v[0] = mk(-hx, -hy); pb.v[1] = mk(hx, -hy); pb.v[2] = mk(hx, hy); pb.v[3] = mk(-hx, hy); }
-                    float t;
-                    bool touching = time_of_impact(ev, pb, sw, t);
-                    if (touching) alpha = min2(alpha0 + (1.0f - alpha0) * t, 1.0f); else alpha = 1.0f;
+                    if (!(Bi(BF_FLAGS, key_body(key)) & BFL_AWAKE)) continue;
+                    alpha = contact_toi(c, key);
                     C(CF_TOI, c) = alpha;
                     setCi(CF_KEY, c, key | (CK_TOIFLAG << 16));
                 }
@@ -1529,13 +1769,14 @@ struct Sim {
         }
     }
 
-    // ---- Modular2D.step + the body of evaluate()'s loop, in three parts so that a whole warp can take over the velocity
-    // iterations of one creature (tail mode): tick_pre -> [solve_velocity | wavefront_velocity] -> tick_post.
+    // ---- Modular2D.step + the body of evaluate()'s loop: tick_pre -> solve_velocity -> tick_post, all group-cooperative.
     // b2World::Step = FindNewContacts (first step) -> Collide -> Solve -> SolveTOI.
     __device__ bool tick_pre(int& nt) {
-        double wod = Sd(S_WOD_LO) + k->wod_speed;
-        setSd(S_WOD_LO, wod);
-        for (int j = 0; j < nj; ++j) {
+        if (leader()) {
+            double wod = Sd(S_WOD_LO) + k->wod_speed;
+            setSd(S_WOD_LO, wod);
+        }
+        for (int j = sub; j < nj; j += G) {
             double ist = Jd(JF_ISTATE, j) + Jd(JF_FREQ, j);
             setJd(JF_ISTATE, j, ist);
             double s, c;
@@ -1544,11 +1785,16 @@ struct Sim {
             int a = Ji(JF_META, j) & 0xff, b = j + 1;
             float currentAngle = B(BF_A, b) - B(BF_A, a) - 0.0f;
             double speed = (out - (double)currentAngle) * k->p_gain;
-            set_awake(a, true); set_awake(b, true);
+            set_awake(a, true); set_awake(b, true);       // (lanes may wake the same body: identical idempotent writes)
             J(JF_MSPEED, j) = (float)speed;
         }
         const float dt = k->dt;
-        if (Si(S_NEWFIX)) { find_new_contacts(); setSi(S_NEWFIX, 0); }
+        const int newfix = bcast(Si(S_NEWFIX));
+        gsync();
+        if (newfix) {
+            if (leader()) { find_new_contacts(); setSi(S_NEWFIX, 0); }
+            gsync();
+        }
         float dtRatio = S(S_INVDT0) * dt;
         collide();
         nt = 0;
@@ -1558,85 +1804,33 @@ struct Sim {
         const float dt = k->dt;
         if (solved) solve_post(nt);
         if (k->continuous && dt > 0.0f) solve_toi();
-        if (dt > 0.0f) S(S_INVDT0) = 1.0f / dt;
-        cnt.c[REM2D_CNT_TICKS]++;
-        int i = Si(S_TICKS);
-        setSi(S_TICKS, i + 1);
-        float x = B(BF_CX, 0);
-        double wod = Sd(S_WOD_LO);
-        double reward = (double)x;
-        if (k->terminate) {
-            if (x < 0.0f) reward = -100.0;
-            if (wod > (double)x) reward = -100.0;
-            if (reward < -10.0) setSi(S_ALIVE, 0);
-            else if (reward > k->env_length) {
-                reward += (double)(k->evaluation_steps - i) / (double)k->evaluation_steps;
-                setSd(S_FIT_LO, reward);
-                setSi(S_ALIVE, 0);
+        if (leader()) {
+            if (dt > 0.0f) S(S_INVDT0) = 1.0f / dt;
+            cnt.c[REM2D_CNT_TICKS]++;
+            int i = Si(S_TICKS);
+            setSi(S_TICKS, i + 1);
+            float x = B(BF_CX, 0);
+            double wod = Sd(S_WOD_LO);
+            double reward = (double)x;
+            if (k->terminate) {
+                if (x < 0.0f) reward = -100.0;
+                if (wod > (double)x) reward = -100.0;
+                if (reward < -10.0) setSi(S_ALIVE, 0);
+                else if (reward > k->env_length) {
+                    reward += (double)(k->evaluation_steps - i) / (double)k->evaluation_steps;
+                    setSd(S_FIT_LO, reward);
+                    setSi(S_ALIVE, 0);
+                } else if (reward > 0.0) setSd(S_FIT_LO, reward);
+                if (i + 1 >= k->evaluation_steps) setSi(S_ALIVE, 0);
             } else if (reward > 0.0) setSd(S_FIT_LO, reward);
-            if (i + 1 >= k->evaluation_steps) setSi(S_ALIVE, 0);
-        } else if (reward > 0.0) setSd(S_FIT_LO, reward);
+        }
+        gsync();
     }
     __device__ void tick() {
         int nt;
         bool solved = tick_pre(nt);
         if (solved) solve_velocity(nt);
         tick_post(solved, nt);
-    }
-
-    // ---- velocity iterations of ONE creature by a whole warp (tail mode): a dependency-respecting wavefront.
-    // Box2D's sequential order within an iteration is: joints in island order, then contacts (newest first); two
-    // constraints commute exactly iff they share no body. Lane l owns constraints l and l+32 of that sequence; a per-body
-    // version counter says how many solves have been applied to the body, and a constraint of iteration `it` may run as
-    // soon as each of its bodies has version it * degree(body) + rank(constraint within the body's sequence). Every
-    // solve therefore reads exactly the velocities it would read in the sequential order — results are bit-identical —
-    // while independent constraints, also of consecutive iterations, run concurrently in different lanes.
-    // `ver` is nb ints of shared memory. Must be called by all 32 lanes.
-    __device__ void wavefront_velocity(int nt, int* ver, int lane) {
-        const int n = nj + nt;
-        const int vit = k->vel_iters;
-        for (int b = lane; b < nb; b += 32) ver[b] = 0;
-        // owned constraints: c0 = lane, c1 = lane + 32 (n <= 64 is guaranteed by the capacity classes: NJ <= 43, nt <= ...)
-        int cA[2], cB[2], rkA[2], rkB[2], dgA[2], dgB[2];
-        int nown = 0;
-        for (int q = 0; q < 2; ++q) {
-            int c = lane + 32 * q;
-            cA[q] = cB[q] = -1; rkA[q] = rkB[q] = dgA[q] = dgB[q] = 0;
-            if (c >= n) continue;
-            nown = q + 1;
-            if (c < nj) { int meta = HJi(HJ_META, c); cA[q] = meta & 0xff; cB[q] = (meta >> 8) & 0xff; }
-            else with_contact(c - nj, [&](float* hc, const int st) { cB[q] = __float_as_int(hc[HC_META * st]) & 0xff; });
-            for (int c2 = 0; c2 < n; ++c2) {
-                int a2 = -1, b2 = -1;
-                if (c2 < nj) { int meta = HJi(HJ_META, c2); a2 = meta & 0xff; b2 = (meta >> 8) & 0xff; }
-                else with_contact(c2 - nj, [&](float* hc, const int st) { b2 = __float_as_int(hc[HC_META * st]) & 0xff; });
-                if (cA[q] >= 0 && (a2 == cA[q] || b2 == cA[q])) { ++dgA[q]; if (c2 < c) ++rkA[q]; }
-                if (a2 == cB[q] || b2 == cB[q]) { ++dgB[q]; if (c2 < c) ++rkB[q]; }
-            }
-        }
-        __syncwarp();
-        int it = 0, q = 0;                 // next owned constraint to run: (iteration it, slot q)
-        const int total = n;
-        (void)total;
-        for (;;) {
-            bool finished = (nown == 0) || (it >= vit);
-            bool ready = false;
-            if (!finished) {
-                ready = ver[cB[q]] == it * dgB[q] + rkB[q];
-                if (cA[q] >= 0) ready = ready && (ver[cA[q]] == it * dgA[q] + rkA[q]);
-            }
-            if (__all_sync(0xffffffffu, finished)) break;
-            __syncwarp();                   // everybody has read the versions of this pass
-            if (ready) {
-                int c = lane + 32 * q;
-                if (c < nj) joint_solve_velocity(c);
-                else with_contact(c - nj, [&](float* hc, const int st) { contact_solve_velocity(hc, st); });
-                if (cA[q] >= 0) ver[cA[q]] += 1;
-                ver[cB[q]] += 1;
-                if (++q == nown) { q = 0; ++it; }
-            }
-            __syncwarp();                   // velocity and version writes are visible before the next pass
-        }
     }
 };
 

@@ -55,14 +55,15 @@ class BatchedModular2D:
         self.engine.upload(table)
 
     def step(self, n_ticks=1):
-        """Advances every living creature by ``n_ticks`` ticks. Returns (reward, done) arrays where
-        reward is the root x or -100 for creatures that hit the termination rule (Modular2DEnv.py:642-649)."""
+        """Advances every living creature by ``n_ticks`` ticks. Returns (reward, done) arrays formed like ``Modular2D.step``
+        (Modular2DEnv.py:642-649): reward = root x, or -100 with done = True when the root is left of the origin or behind the
+        wall of death. A creature whose episode ended with success (x > ENV_LENGTH) or at the step limit keeps reporting its
+        x — only the two death rules give -100, as in the reference."""
         self.engine.step(n_ticks)
-        st = self.engine.read_state()
-        root = self.table.body_off[:-1]
-        x = st["pose"][root, 0].astype(np.float64)
-        done = st["alive"] == 0
-        return np.where(done, -100.0, x), done
+        x, wod, _alive = self.engine.read_roots()          # 16 bytes per creature, not the whole state block
+        x = x.astype(np.float64)
+        dead = (x < 0.0) | (wod > x)
+        return np.where(dead, -100.0, x), dead
 
     def fitness(self):
         return self.engine.fitness()

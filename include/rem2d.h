@@ -166,6 +166,14 @@ float rem2d_last_step_ms(rem2d_handle* h);
 int rem2d_measure_fp32_peak(rem2d_handle* h, double* gflops);
 /* Number of kernels this library launched since rem2d_create. */
 int64_t rem2d_launch_count(rem2d_handle* h);
+/* Tuning / diagnostic option by name (execution strategy only, never results): "warp_mode_max", "park_ticks", "park_cap",
+ * "smem_budget_kb", "small_weight", "min_class", "group_shift", "tail_group_shift", "trace", "phased" (DESIGN.md section 4).
+ * Unknown names return REM2D_E_INVALID. The oracle accepts the same names and ignores them. */
+int rem2d_set_option(rem2d_handle* h, const char* name, double value);
+/* Cheap per-creature read-out for step-wise drivers (what Modular2D.step needs to form its reward, Modular2DEnv.py:642-649):
+ * root x (= robot.components[0].position[0]), wall-of-death position, alive flag. Any pointer may be NULL. Valid after
+ * rem2d_upload / rem2d_reset / rem2d_step. */
+int rem2d_read_roots(rem2d_handle* h, float* root_x, double* wod, int32_t* alive);
 
 #ifdef __cplusplus
 }

@@ -2187,3 +2187,23 @@ int rem2d_evaluate(rem2d_handle* h, const rem2d_population* pop, int32_t max_tic
 int rem2d_measure_fp32_peak(rem2d_handle* h, double* gflops) { (void)h; if (gflops) *gflops = 0.0; return REM2D_E_INVALID; }
 float rem2d_last_step_ms(rem2d_handle* h) { (void)h; return 0.0f; }
 int64_t rem2d_launch_count(rem2d_handle* h) { (void)h; return 0; }
+/* execution-strategy options of the CUDA build: accepted and ignored (they never change results) */
+int rem2d_set_option(rem2d_handle* h, const char* name, double value) {
+    static const char* known[] = {"warp_mode_max", "park_ticks", "park_cap", "smem_budget_kb", "small_weight", "min_class",
+                                  "group_shift", "tail_group_shift", "trace", "phased"};
+    (void)value;
+    if (!h || !name) return REM2D_E_INVALID;
+    for (size_t i = 0; i < sizeof(known) / sizeof(known[0]); ++i) if (!strcmp(known[i], name)) return REM2D_OK;
+    snprintf(h->err, sizeof(h->err), "set_option: unknown option %s", name);
+    return REM2D_E_INVALID;
+}
+int rem2d_read_roots(rem2d_handle* h, float* root_x, double* wod, int32_t* alive) {
+    if (!h || !h->have_pop) return REM2D_E_INVALID;
+    for (int c = 0; c < h->n_worlds; ++c) {
+        World* w = &h->worlds[c];
+        if (root_x) root_x[c] = w->bodies[0].xf.p.x;
+        if (wod) wod[c] = w->wod;
+        if (alive) alive[c] = w->alive;
+    }
+    return REM2D_OK;
+}
