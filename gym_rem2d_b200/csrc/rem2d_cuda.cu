@@ -159,6 +159,7 @@ struct Options {
     double smem_budget_kb = 227.0, small_weight = 1.0;
     int min_class = 0;
     int group_shift = -1;        // log2 lanes per creature in the queue / step kernels (-1: per class default)
+    int class_gs[N_CLASSES] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per capacity class ("class_gs_<k>", -1: default)
     int tail_group_shift = 5;    // log2 lanes per creature of the tail launches
     int trace = 0;
     int phased = 0;              // tick phases with survivor compaction instead of the persistent queue kernel
@@ -214,7 +215,7 @@ static thread_local std::string g_create_err;
     } while (0)
 
 static int class_gs(const rem2d_handle* h, int k) {
-    int gs = h->opt.group_shift >= 0 ? h->opt.group_shift : g_classes(k).gs;
+    int gs = h->opt.group_shift >= 0 ? h->opt.group_shift : (h->opt.class_gs[k] >= 0 ? h->opt.class_gs[k] : g_classes(k).gs);
     return gs < 0 ? 0 : (gs > 5 ? 5 : gs);
 }
 static bool set_option(Options& o, const char* name, double v) {
@@ -229,6 +230,7 @@ static bool set_option(Options& o, const char* name, double v) {
     else if (n == "tail_group_shift") o.tail_group_shift = std::max(0, std::min(5, (int)v));
     else if (n == "trace") o.trace = (int)v;
     else if (n == "phased") o.phased = (int)v;
+    else if (n.rfind("class_gs_", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] < '0' + N_CLASSES) o.class_gs[n[9] - '0'] = (int)v;
     else return false;
     return true;
 }
@@ -241,6 +243,8 @@ static void options_from_env(Options& o) {
         if (const char* e = getenv(env.c_str())) set_option(o, n, atof(e));
     }
     if (const char* e = getenv("REM2D_EPISODE_MODE")) o.phased = !strcmp(e, "phased");
+    if (const char* e = getenv("REM2D_CLASS_GS"))          // "0,0,1,2,2,2,2,3,3": group shift per capacity class
+        for (int k = 0; k < N_CLASSES && *e; ++k) { o.class_gs[k] = atoi(e); while (*e && *e != ',') ++e; if (*e == ',') ++e; }
 }
 
 static void free_population(rem2d_handle* h) {          // logical reset; the buffers stay allocated for reuse

@@ -168,6 +168,9 @@ enum { CF_KEY, CF_TOI, CF_LNX, CF_LNY, CF_LPX, CF_LPY, CF_P0X, CF_P0Y, CF_P0N, C
 #define MT_CIRCLES 0
 #define MT_FACE_A 1
 #define MT_FACE_B 2
+// HJ_META / PJ_META: a | b << 8 | limit << 16 | flags | j << 24; flags: this joint is the last one of its body A (B) in island order
+#define HJM_LAST_A (1 << 18)
+#define HJM_LAST_B (1 << 19)
 // status bits
 #define ST_POOL_OVERFLOW 1     // contact pool (NC) exhausted
 
@@ -210,9 +213,10 @@ struct Cnt { unsigned int c[REM2D_N_COUNTERS]; };   // per lane per launch; summ
 // Within a section the words are element-major (element * FIELD_COUNT + field), so that field offsets are immediates.
 struct Layout {
     int nb, nj, nc, nt;                        // bodies, joints, contact-pool slots, hot (shared memory) touching contacts
-    int off_joint, off_cont, off_edge, off_spill, words;      // cold block, words per lane (bodies start at S_COUNT)
+    int off_joint, off_cont, off_edge, off_spill, off_ring, words;      // cold block, words per lane (bodies start at S_COUNT)
     int hot_words;                                            // hot block with one lane per creature, words per lane
 };
+#define RB_RING 8             // end-of-iteration body poses kept by the pipelined position sweeps (iterations in flight)
 #define RB_SCHED_ROWS 20      // slots per period of the static schedule (shared-memory rows per warp); longer periods fall back
 #define RB_MAX_SKEW 24        // iteration skew bound of a schedule (ring depth of the position-phase end-of-iteration states)
 __host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
@@ -222,7 +226,8 @@ __host__ __device__ inline Layout make_layout(int NB, int NC, int NT) {
     L.off_cont = L.off_joint + JF_COUNT * L.nj;
     L.off_edge = L.off_cont + CF_COUNT * NC;                  // alpha0 of the static edge bodies
     L.off_spill = L.off_edge + RB_MAX_EDGES;                  // touching contacts beyond NT spill to HBM
-    L.words = L.off_spill + HC_COUNT * (NC - NT);
+    L.off_ring = L.off_spill + HC_COUNT * (NC - NT);          // RB_RING x NB x (cx, cy, a)
+    L.words = L.off_ring + RB_RING * 3 * NB;
     L.hot_words = HB_COUNT * NB + HJ_COUNT * L.nj + HC_COUNT * NT;
     return L;
 }
@@ -279,6 +284,7 @@ struct Sim {
     __device__ __forceinline__ int Ci(int f, int c) { return __float_as_int(C(f, c)); }
     __device__ __forceinline__ void setCi(int f, int c, int v) { C(f, c) = __int_as_float(v); }
     __device__ __forceinline__ float& EA(int e) { return g[(L.off_edge + e) * 32]; }
+    __device__ __forceinline__ float& RING(int r, int b, int f) { return g[(L.off_ring + (r * L.nb + b) * 3 + f) * 32]; }
     // lane = lane index in the warp; hot = the warp's hot block
     __device__ __forceinline__ void set_group(int gshift, int lane, float* hot) {
         gs = gshift; G = 1 << gs; sub = lane & (G - 1); lead = lane & ~(G - 1);
@@ -889,13 +895,14 @@ struct Sim {
         }
     }
     // one pass of Solve(TOI)PositionConstraints over hot slot t; returns the min separation seen
+    template <bool COUNT = true>
     __device__ __forceinline__ float contact_solve_position(float* hc, const int st, float baumgarte, float minSeparation) {
         int meta = __float_as_int(hc[PC_META * st]);
         int b = meta & 0xff, count = (meta >> 8) & 3, type = (meta >> 10) & 3;
         float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
         V2 cB = mk(HB(HB_VX, b), HB(HB_VY, b)); float aB = HB(HB_W, b);     // position overlay: c, a
         for (int j = 0; j < count; ++j) {
-            cnt.c[REM2D_CNT_POINT_PSOLVES]++;
+            if (COUNT) cnt.c[REM2D_CNT_POINT_PSOLVES]++;
             V2 normal, point;
             float separation = psm(hc, st, type, j, cB, aB, normal, point);
             V2 rB = point - cB;
@@ -1148,6 +1155,16 @@ struct Sim {
                 HB(HB_VX, a) = vA.x; HB(HB_VY, a) = vA.y; HB(HB_W, a) = wA;
                 HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
             }
+            if (gs) {      // the last joint of every body in island order (it closes the body's position iteration, see solve_post)
+                unsigned long long seen = 0ull;
+                for (int s = nj - 1; s >= 0; --s) {
+                    int meta = HJi(HJ_META, s);
+                    const int a = meta & 0xff, b = (meta >> 8) & 0xff;
+                    if (!((seen >> a) & 1ull)) { meta |= HJM_LAST_A; seen |= 1ull << a; }
+                    if (!((seen >> b) & 1ull)) { meta |= HJM_LAST_B; seen |= 1ull << b; }
+                    HJ(HJ_META, s) = __int_as_float(meta);
+                }
+            }
         }
         nt_out = nt;
         build_schedule(nt, false);
@@ -1341,19 +1358,69 @@ struct Sim {
         }
         gsync();
         int positionSolved = 0;
-        if (leader()) {
-            const int pit = k->pos_iters;
-            for (int it = 0; it < pit; ++it) {
-                float minSep = 0.0f;
-                for_contacts(nt, [&](float* hc, const int st, int) { minSep = contact_solve_position(hc, st, RB_BAUMGARTE, minSep); });
-                bool contactsOkay = minSep >= -3.0f * RB_LINEAR_SLOP;
-                bool jointsOkay = true;
-                for (int s = 0; s < nj; ++s) { bool ok = joint_solve_position(s); jointsOkay = jointsOkay && ok; }
-                cnt.c[REM2D_CNT_JOINT_PSOLVES] += (unsigned)nj;
-                if (contactsOkay && jointsOkay) { positionSolved = 1; break; }
+        const int pit = k->pos_iters;
+        const int psmax = sched_smax + (nt > 0 ? 1 : 0);
+        if (sched_P && nj > 0 && psmax < RB_RING && pit <= 64) {      // (nj > 0: every body has a joint that files its pose)
+            // Pipelined position iterations on the velocity schedule. A position sweep solves the contacts first and the joints
+            // after them, i.e. every body sees the SAME cyclic order of its constraints as in a velocity sweep, only the
+            // iteration starts at its contacts: the schedule is reused with the joints one period later than the contacts
+            // (skew + 1). Box2D stops after the first iteration in which every constraint was within tolerance, which is only
+            // known when the slowest-skewed constraint has finished that iteration - lanes have then run ahead by up to
+            // psmax iterations. Every body therefore files its pose at the end of each iteration (after its last joint) in a
+            // ring of RB_RING entries, and on convergence at iteration K the poses of iteration K are restored: exactly the
+            // state of the sequential loop at its break.
+            const int P = sched_P;
+            unsigned long long bad = 0ull;        // bit it: one of MY constraints was out of tolerance in iteration it
+            int stopK = -1;
+            for (int T = 0; T < pit + psmax && stopK < 0; ++T) {
+                for (int pslot = 0; pslot < P; ++pslot) {
+                    const int e = SCH(pslot, sub);
+                    const bool isc = (e & SCH_CONTACT) != 0;
+                    const int it = T - ((e >> 8) & 0xff) - (isc || nt == 0 ? 0 : 1);
+                    const bool act = e < 0 && it >= 0 && it < pit;
+                    if (act && isc) {
+                        const float ms = contact_solve_position<false>(hot_elem(hc_off, HC_COUNT, e & 0xff), 32, RB_BAUMGARTE, 0.0f);
+                        if (!(ms >= -3.0f * RB_LINEAR_SLOP)) bad |= 1ull << it;
+                    }
+                    if (act && !isc) {
+                        const int sj = e & 0xff;
+                        if (!joint_solve_position(sj)) bad |= 1ull << it;
+                        const int meta = HJi(PJ_META, sj);
+                        if (meta & HJM_LAST_A) { const int a = meta & 0xff; RING(it & (RB_RING - 1), a, 0) = HB(HB_VX, a); RING(it & (RB_RING - 1), a, 1) = HB(HB_VY, a); RING(it & (RB_RING - 1), a, 2) = HB(HB_W, a); }
+                        if (meta & HJM_LAST_B) { const int b = (meta >> 8) & 0xff; RING(it & (RB_RING - 1), b, 0) = HB(HB_VX, b); RING(it & (RB_RING - 1), b, 1) = HB(HB_VY, b); RING(it & (RB_RING - 1), b, 2) = HB(HB_W, b); }
+                    }
+                    gsync();
+                }
+                const int d = T - psmax;          // every constraint has finished iteration d
+                if (d >= 0 && !group_any(((bad >> d) & 1ull) != 0ull)) stopK = d;
             }
+            const int iters = stopK >= 0 ? stopK + 1 : pit;
+            positionSolved = stopK >= 0 ? 1 : 0;
+            if (stopK >= 0 && psmax > 0)
+                for (int b = sub; b < nb; b += G) {
+                    HB(HB_VX, b) = RING(stopK & (RB_RING - 1), b, 0); HB(HB_VY, b) = RING(stopK & (RB_RING - 1), b, 1);
+                    HB(HB_W, b) = RING(stopK & (RB_RING - 1), b, 2);
+                }
+            if (leader()) {
+                cnt.c[REM2D_CNT_JOINT_PSOLVES] += (unsigned)(iters * nj);
+                int points = 0;
+                for (int t = 0; t < nt; ++t) points += (__float_as_int(hot_elem(hc_off, HC_COUNT, t)[PC_META * 32]) >> 8) & 3;
+                cnt.c[REM2D_CNT_POINT_PSOLVES] += (unsigned)(iters * points);
+            }
+        } else {
+            if (leader()) {
+                for (int it = 0; it < pit; ++it) {
+                    float minSep = 0.0f;
+                    for_contacts(nt, [&](float* hc, const int st, int) { minSep = contact_solve_position(hc, st, RB_BAUMGARTE, minSep); });
+                    bool contactsOkay = minSep >= -3.0f * RB_LINEAR_SLOP;
+                    bool jointsOkay = true;
+                    for (int s = 0; s < nj; ++s) { bool ok = joint_solve_position(s); jointsOkay = jointsOkay && ok; }
+                    cnt.c[REM2D_CNT_JOINT_PSOLVES] += (unsigned)nj;
+                    if (contactsOkay && jointsOkay) { positionSolved = 1; break; }
+                }
+            }
+            positionSolved = bcast(positionSolved);
         }
-        positionSolved = bcast(positionSolved);
         gsync();
         // copy back, synchronize transforms, sleep management
         float minSleepTime = RB_MAXF;

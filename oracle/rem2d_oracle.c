@@ -2194,6 +2194,7 @@ int rem2d_set_option(rem2d_handle* h, const char* name, double value) {
     (void)value;
     if (!h || !name) return REM2D_E_INVALID;
     for (size_t i = 0; i < sizeof(known) / sizeof(known[0]); ++i) if (!strcmp(known[i], name)) return REM2D_OK;
+    if (!strncmp(name, "class_gs_", 9) && strlen(name) == 10) return REM2D_OK;
     snprintf(h->err, sizeof(h->err), "set_option: unknown option %s", name);
     return REM2D_E_INVALID;
 }

@@ -276,3 +276,56 @@ def test_config4_4096_cppn_ce_rough():
     fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
     assert np.array_equal(tg, to) and np.array_equal(fg, fo)
     assert g.counters() == co
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Lanes per creature (group shift): the same kernels with G = 1, 2, 4, 8, 32 lanes per creature must all equal the oracle.
+@pytest.mark.parametrize("gs", ["0", "1", "2", "3", "5"])
+def test_every_group_size_stepping_kernel_bit_exact(gs, monkeypatch):
+    monkeypatch.setenv("REM2D_GROUP_SHIFT", gs)
+    random.seed(81)
+    pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(160)])
+    xs, ys = terrain.generate_terrain()
+    g, o = engines(ys)
+    g.upload(pop); o.upload(pop)
+    for t in (1, 9, 40, 60):
+        g.step(t); o.step(t)
+        assert_same_state(g.read_state(max_pairs=24), o.read_state(max_pairs=24), "gs=%s after +%d" % (gs, t))
+    assert g.counters() == o.counters()
+
+
+@pytest.mark.parametrize("gs,tail_gs", [("0", "5"), ("1", "3"), ("2", "5"), ("3", "4"), ("4", "2")])
+def test_every_group_size_queue_and_tail_modes_full_episodes(gs, tail_gs, monkeypatch):
+    from gym_rem2d_b200.population import random_population
+    pop = random_population(1536, ("lsystem",), seed=83, workers=4)
+    xs, ys = terrain.generate_terrain()
+    fo, to, co = _oracle_eval(pop, ys)
+    monkeypatch.setenv("REM2D_GROUP_SHIFT", gs)
+    monkeypatch.setenv("REM2D_TAIL_GROUP_SHIFT", tail_gs)
+    monkeypatch.setenv("REM2D_WARP_MODE_MAX", "0")
+    monkeypatch.setenv("REM2D_SMEM_BUDGET_KB", "30")
+    monkeypatch.setenv("REM2D_PARK_TICKS", "130")
+    monkeypatch.setenv("REM2D_PARK_CAP", "0.1")
+    g = Engine(device=0)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to), "ticks differ for %d creatures" % (tg != to).sum()
+    assert np.array_equal(fg, fo)
+    assert g.counters() == co
+
+
+def test_set_option_and_read_roots():
+    random.seed(91)
+    pop = flatten_population([Individual.random(encoding="direct") for _ in range(40)])
+    xs, ys = terrain.generate_terrain()
+    g, o = engines(ys)
+    g.set_option("group_shift", 2)
+    with pytest.raises(Exception):
+        g.set_option("no_such_option", 1)
+    g.upload(pop); o.upload(pop)
+    g.step(50); o.step(50)
+    xg, wg, ag = g.read_roots()
+    xo, wo, ao = o.read_roots()
+    assert np.array_equal(xg, xo) and np.array_equal(wg, wo) and np.array_equal(ag, ao)
+    root = pop.body_off[:-1]
+    assert np.array_equal(xg, g.read_state()["pose"][root, 0])
