@@ -2063,6 +2063,28 @@ int rem2d_reset(rem2d_handle* h) {
     return REM2D_OK;
 }
 
+/* TEST-ONLY entry point of the oracle-backed Box2D shim (tests/golden/oracle_box2d.py): what the reference's Modular2D.step
+ * does to the world between its own Python statements - `joint.motorSpeed = v` for every joint (b2RevoluteJoint::SetMotorSpeed
+ * wakes both bodies, Modular2DEnv.py:631-632) followed by ONE world.Step (Modular2DEnv.py:634). No controllers, no wall of
+ * death, no episode bookkeeping: the reference's unmodified Python does those around this call. */
+int rem2d_oracle_world_step(rem2d_handle* h, int creature, const float* motor_speed, int n_joints) {
+    if (!h || !h->have_pop || creature < 0 || creature >= h->n_worlds) return REM2D_E_INVALID;
+    World* w = &h->worlds[creature];
+    if (n_joints != w->nj) return REM2D_E_INVALID;
+    g_sincos_mode = h->cfg.sincos_mode;
+    Counters cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    for (int k = 0; k < w->nj; ++k) {
+        Joint* j = &w->joints[k];
+        body_set_awake(&w->bodies[j->bodyA], 1);
+        body_set_awake(&w->bodies[j->bodyB], 1);
+        j->motorSpeed = motor_speed[k];
+    }
+    world_step(h, w, &cnt);
+    for (int i = 0; i < REM2D_N_COUNTERS; ++i) h->counters[i] += cnt.c[i];
+    return REM2D_OK;
+}
+
 int rem2d_oracle_set_threads(rem2d_handle* h, int n) { if (!h) return REM2D_E_INVALID; h->threads = n; return REM2D_OK; }
 
 typedef struct { rem2d_handle* h; int n_ticks; int* next; Counters cnt; } StepJob;

@@ -14,7 +14,7 @@ e = Engine(device=0)
 e.set_terrain(ys, K.TERRAIN_STEP)
 e.upload(pop)
 e.run_episodes(10000)
-os.environ["REM2D_TRACE"] = "1"
+e.set_option("trace", 1)
 e.run_episodes(10000)
 print("traced run: %.0f ms, %d creature-steps" % (e.last_step_ms(), e.ticks().sum()))
 S = 1024
@@ -57,6 +57,6 @@ for k, a in traces.items():
                     lat.append(np.median(d))
         rows.append((b0, running, lanes, float(np.median(lat)) if lat else 0.0))
     for b0, running, lanes, lat in rows:
-        print("   t=%4d ms  warps running %4d  live lanes %7.0f (%.0f%% of %d)  tick latency %.2f ms"
+        print("   t=%4d ms  warps running %4d  live lanes %7.0f (%.0f%% of %d lanes/creatures)  tick latency %.2f ms"
               % (b0, running, lanes, 100.0 * lanes / (nw * 32), nw * 32, lat))
 np.savez_compressed("gpurun_out/trace.npz", **{"c%d" % k: v for k, v in traces.items()})
