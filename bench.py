@@ -229,6 +229,32 @@ def main():
         e2e_s, e2e_steps = float(a[0]), float(b[1])
     e2e_value = e2e_steps / e2e_s
 
+    # -- strong scaling (N > 1): ONE population of args.pop creatures sharded over the ranks through the product API
+    # (distributed.shard_population -> rem2d_evaluate -> distributed.gather_fitness over NCCL), everything inside the timed
+    # region: what replaces pool.map(evaluate, population, chunksize=...) of REM2D_main.py:256-262 at BASELINE's stated size.
+    strong = None
+    if world > 1:
+        from gym_rem2d_b200 import distributed as rdist
+        whole = random_population(args.pop, encodings, seed=args.seed, workers=1, cache_dir=cache)    # rank 0's population (cached)
+        rdist.evaluate_sharded(whole, eng, K.EVALUATION_STEPS, device=dev)                               # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        s_steps = 0
+        for _ in range(args.steps):
+            fit_strong, st_ = rdist.evaluate_sharded(whole, eng, K.EVALUATION_STEPS, device=dev)
+            s_steps += st_
+        barrier()
+        s_s = time.perf_counter() - t0
+        ts = torch.tensor([s_s, float(s_steps)], dtype=torch.float64, device=dev)
+        a = ts.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = ts.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        strong = {"value": float(b[1]) / float(a[0]), "unit": "creature-steps/s", "ms_per_step": float(a[0]) / args.steps * 1e3,
+                  "population_total": args.pop, "population_per_gpu": args.pop // world, "scaling": "strong",
+                  "path": "distributed.shard_population -> rem2d_evaluate (host buffers) -> distributed.gather_fitness (NCCL all_gather) "
+                          "inside the timed region",
+                  # rank 0's weak-scaling population IS this population: the gathered vector must equal its single-GPU result
+                  "identical_to_single_gpu": bool(np.array_equal(fit_strong, fit.astype(np.float32))) if rank == 0 else None}
+
     if rank == 0:
         # roofline of the dominant kernel (step_kernel): algorithmic work of one evaluation / its device time
         step_ms = kernel_ms / args.steps
@@ -260,7 +286,7 @@ def main():
                 "clocks": clocks.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "creature-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "roofline": roofline, "fp32_issue": fp32,
-                "counters": counters, "fitness": {"mean": float(np.mean(fit_all)), "max": float(np.max(fit_all)), "n": int(len(fit_all))},
+                "strong_scaling": strong, "counters": counters, "fitness": {"mean": float(np.mean(fit_all)), "max": float(np.max(fit_all)), "n": int(len(fit_all))},
                 "mean_ticks_per_creature": creature_steps / pop.n_creatures}
         if not args.no_cpu_baseline and world == 1:
             sample = min(args.pop, max(256, 1800 * cores))      # ~10 s of CPU work

@@ -16,6 +16,11 @@ class Controller:
     def __init__(self):
         self.i_state = 0
         self.output = 0
+        # instance copies of the bounds, like the reference's __init__ (m_controller.py:9-12): part of the pickled state
+        self.MAX_AMP = 1
+        self.MAX_PHASE = 1
+        self.MAX_OFFSET = math.pi
+        self.MAX_FREQ = 0.1
         self.amplitude = random.uniform(0, self.MAX_AMP)
         self.phase = random.uniform(-self.MAX_PHASE, self.MAX_PHASE)
         self.frequency = random.uniform(-self.MAX_FREQ, self.MAX_FREQ)

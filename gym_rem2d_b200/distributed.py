@@ -50,13 +50,17 @@ def gather_fitness(local_fitness, local_idx, n_total, device=None):
     return out
 
 
-def evaluate_sharded(table, make_engine, max_ticks, rank=None, world=None):
-    """Evaluate this rank's shard of ``table`` with ``make_engine()`` and gather everyone's fitness."""
+def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=None):
+    """Evaluate this rank's shard of ``table`` on ``engine`` and gather everyone's fitness: the multi-GPU form of
+    ``pool.map(evaluate, population, chunksize=ceil(pop/n))`` (REM2D_main.py:256-262). ``engine`` is a long-lived
+    ``capi.Engine`` (its device buffers are grow-only and reused from generation to generation); a zero-argument factory is
+    accepted for one-off calls. Returns (fitness of the WHOLE population in population order, float32; this rank's
+    creature-steps)."""
     import torch.distributed as dist
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
         world = dist.get_world_size() if dist.is_initialized() else 1
     sub, idx = shard_population(table, rank, world)
-    eng = make_engine()
+    eng = engine() if callable(engine) else engine
     fit, ticks = eng.evaluate(sub, max_ticks)
-    return gather_fitness(fit, idx, table.n_creatures), int(ticks.sum())
+    return gather_fitness(fit, idx, table.n_creatures, device=device), int(ticks.sum())

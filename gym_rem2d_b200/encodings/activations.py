@@ -47,19 +47,32 @@ CPPN_ORDER = ['abs', 'clamped', 'cube', 'exp', 'gauss', 'hat', 'identity', 'inv'
 
 
 class Activation:
-    """Picklable handle on an activation (the reference stores bare functions)."""
+    """Picklable handle on an activation, one instance per name (the reference stores the bare functions of
+    NeuralNetwork/activations.py, which pickle by name; refpickle.dump writes these handles under those names)."""
     __slots__ = ("name",)
+    _instances = {}
+    reference_names = False        # set by refpickle.reference_class_paths()
 
-    def __init__(self, name):
-        if name not in FUNCTIONS:
-            raise TypeError("No such activation function: {0!r}".format(name))
-        self.name = name
+    def __new__(cls, name):
+        inst = cls._instances.get(name)
+        if inst is None:
+            if name not in FUNCTIONS:
+                raise TypeError("No such activation function: {0!r}".format(name))
+            inst = object.__new__(cls)
+            inst.name = name
+            cls._instances[name] = inst
+        return inst
 
     def __call__(self, z):
         return FUNCTIONS[self.name](z)
 
-    def __getstate__(self):
-        return self.name
+    def __reduce__(self):
+        if Activation.reference_names:
+            return self.name + "_activation"          # global NeuralNetwork.activations.<name>_activation
+        return (Activation, (self.name,))
 
-    def __setstate__(self, s):
-        self.name = s
+    def __deepcopy__(self, memo):
+        return self
+
+    def __copy__(self):
+        return self

@@ -6,12 +6,18 @@ here?, which type, its morphology parameters and its four sine-controller parame
 only evaluated at expansion time — at run time the creature is driven by plain sine controllers.
 """
 import copy
+from enum import Enum
 
 from .. import tree as _tree
 from . import cellular
 from . import cppn as _cppn
 
 MAX_MODULES = 20
+
+
+class NETWORK_TYPE(Enum):          # Network_Encoding.py:18-20 (kept as an Enum so that pickles are interchangeable)
+    CPPN = 0
+    CE = 1
 
 
 class C_Module:
@@ -40,7 +46,9 @@ class NN_enc:
         else:
             self.maxTreeDepth = 7
             self.maxModules = 20
-        self.networkType = type
+        if type not in ("CPPN", "CE"):
+            raise Exception("Cannot create network encoding, unknown network type %r" % (type,))
+        self.networkType = NETWORK_TYPE.CPPN if type == "CPPN" else NETWORK_TYPE.CE
         if type == "CPPN":
             self.nn_g = _cppn.CPPN(n_inputs, n_outputs, t_config=config)
         elif type == "CE":
@@ -51,9 +59,9 @@ class NN_enc:
             mod.mutate(0.5, 0.5, 0.5)
 
     def _query(self, inputs):
-        if self.networkType == "CPPN":
+        if self.networkType == NETWORK_TYPE.CPPN:
             return list(self.nn_p.activate(inputs))
-        if self.networkType == "CE":
+        if self.networkType == NETWORK_TYPE.CE:
             return self.nn_p.update(inputs, requested_number_of_outputs=9)
         raise Exception("Cannot update network, no network type found")
 
@@ -88,9 +96,9 @@ class NN_enc:
         return index, new_symbols
 
     def mutate(self, MORPH_MUTATION_RATE, MUTATION_RATE, MUT_SIGMA, TREE_DEPTH=None):
-        if self.networkType == "CPPN":
+        if self.networkType == NETWORK_TYPE.CPPN:
             self.nn_g.mutate()
-        elif self.networkType == "CE":
+        elif self.networkType == NETWORK_TYPE.CE:
             self.nn_g.mutate(MORPH_MUTATION_RATE, MUTATION_RATE, MUT_SIGMA)
             self.nn_g.create()
         for mod in self.moduleList:
@@ -111,10 +119,10 @@ class NN_enc:
 
     def create(self, treedepth):
         self.maxTreeDepth = treedepth
-        if self.networkType == "CE":
+        if self.networkType == NETWORK_TYPE.CE:
             self.nn_g.create()
             self.nn_p = self.nn_g
-        elif self.networkType == "CPPN":
+        elif self.networkType == NETWORK_TYPE.CPPN:
             self.nn_p = self.nn_g.getPhenotype()
         base = C_Module(0, self.moduleList[0], -1)      # the root's type is -1 (Network_Encoding.py:189)
         base.controller = copy.deepcopy(self.moduleList[0].controller)

@@ -9,6 +9,8 @@ import math
 import random
 from enum import Enum
 
+import numpy as np
+
 from .controller import Controller
 
 
@@ -49,13 +51,25 @@ class Standard2D(Module):
     MAX_ANGLE = math.pi
     MIN_ANGLE = 0
 
-    def __init__(self):
+    def __init__(self, theta=0, size=(0.1, 0.1, 0.0)):
+        # the instance carries every attribute the reference's __init__ sets (simple_module.py:29-53), bounds included, so
+        # that a pickled module is a complete state for the reference's class as well (refpickle.py)
+        self.theta = theta % 2
+        self.size = np.array(size)
+        self.position = np.array([0., self.size[2] / 2. + 0.002, 0.])
         self.connection_type = Connection
         self._children = {}
         self.controller = Controller()
         self.width = 0.2
         self.height = 0.8
         self.angle = math.pi / 2
+        self.type = "SIMPLE"
+        self.MAX_HEIGHT = 1.0
+        self.MIN_HEIGHT = 0.5
+        self.MAX_WIDTH = 1.0
+        self.MIN_WIDTH = 0.5
+        self.MAX_ANGLE = math.pi
+        self.MIN_ANGLE = 0
         self.torque = 50
 
     def limitWH(self):
@@ -127,11 +141,21 @@ class Circular2D(Module):
     MIN_ANGLE = math.pi / 4
     MAX_ANGLE = math.pi * 2
 
-    def __init__(self):
+    def __init__(self, theta=0, size=(0.1, 0.1, 0.0)):
+        # every attribute of the reference's __init__ (circular_module.py:31-53) except connection_axis / orientation, which
+        # are gym_rem (3-D tree) objects only touched by the dead 3-D methods of the reference class
+        self.theta = theta % 2
+        self.size = np.array(size)
+        self.position = np.array([0., self.size[2] / 2. + 0.002, 0.])
         self._children = {}
         self.controller = Controller()
         self.radius = 0.25
         self.angle = math.pi / 2
+        self.type = "CIRCLE"
+        self.MIN_RADIUS = 0.25
+        self.MAX_RADIUS = 0.5
+        self.MIN_ANGLE = math.pi / 4
+        self.MAX_ANGLE = math.pi * 2
         self.torque = 50
 
     def limitWH(self):
