@@ -128,6 +128,7 @@ struct ClassState {
     int n_batches = 0;
     int n_members = 0;                  // creatures of this class (lane_creature[0..n_members) are real)
     int episode_grid = 0;               // resident warps of the persistent episode kernel
+    double work = 0.0;                  // sum of the per-creature cost estimates (grid sizing)
     float* d_state = nullptr;
     int* d_lane_creature = nullptr;
     int* d_queue = nullptr;
@@ -168,6 +169,7 @@ struct Options {
 struct rem2d_handle {
     rem2d_config cfg;
     Options opt;
+    int cur_gs[N_CLASSES] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // lanes per creature (log2) of the queue mode, per class
     cudaStream_t user_stream = nullptr;
     Terrain* d_ter = nullptr;
     Consts* d_consts = nullptr;
@@ -184,6 +186,7 @@ struct rem2d_handle {
     bool state_valid = false;           // per-creature state blocks hold a consistent snapshot (reset/step path)
     bool results_valid = false;         // d_fitness/d_ticks/... were written by the episode kernel
     int n_sms = 0;
+    int max_warps_per_sm = 16;          // resident warps of the episode kernel per SM by registers (occupancy API)
     int n_edges = 0;
     // population
     int n_creatures = 0, n_bodies = 0, n_joints = 0;
@@ -214,9 +217,18 @@ static thread_local std::string g_create_err;
         }                                                                                                \
     } while (0)
 
-static int class_gs(const rem2d_handle* h, int k) {
-    int gs = h->opt.group_shift >= 0 ? h->opt.group_shift : (h->opt.class_gs[k] >= 0 ? h->opt.class_gs[k] : g_classes(k).gs);
-    return gs < 0 ? 0 : (gs > 5 ? 5 : gs);
+// group shift of class k for the QUEUE mode of the uploaded population (choose_groups_and_grids)
+static int class_gs(const rem2d_handle* h, int k) { return h->cur_gs[k]; }
+// group shift of the stepping kernels (rem2d_reset / rem2d_step: static creature -> column mapping, no residency limit): the
+// option if given, else as wide as keeps all warps of the population resident at once (a single creature gets a whole warp)
+static int step_gs(const rem2d_handle* h, int k) {
+    const int o = h->opt.group_shift >= 0 ? h->opt.group_shift : h->opt.class_gs[k];
+    if (o >= 0) return std::min(5, o);
+    int total = 0;
+    for (int q = 0; q < N_CLASSES; ++q) total += h->cls[q].n_batches;
+    int gs = 0;
+    while (gs < 5 && (total << (gs + 1)) <= h->n_sms * 8) ++gs;
+    return g_classes(k).nb <= 2 ? 0 : gs;
 }
 static bool set_option(Options& o, const char* name, double v) {
     const std::string n(name);
@@ -334,6 +346,7 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
         for (int q = 0; q < N_CLASSES; ++q)
             for (int gs = 0; gs <= 5; ++gs) max_hot = std::max(max_hot, g_classes(q).hot_bytes(gs));
         if ((e = rem2d_set_kernel_attributes(max_hot, carve)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
+        h->max_warps_per_sm = std::max(1, rem2d_episode_blocks_per_sm(1024));
     }
     *out = h;
     return REM2D_OK;
@@ -401,6 +414,89 @@ static cudaError_t upload_array(rem2d_handle* h, int slot, const T* src, size_t 
 }
 
 static int launch_reset(rem2d_handle* h);
+
+// Resident warps of the persistent episode kernels for the current group shifts (h->cur_gs). All classes run concurrently, so
+// the shared memory of the SMs (227 KB each) and the resident-warp limit set by the register file are divided among them in
+// proportion to their work; a class never gets more warps than it has creatures, and what it cannot use is handed to the
+// others. Without this the largest class would occupy every SM until its last creature dies and the remaining classes would
+// run after it. Returns true iff EVERY creature of every class has a group from the start (one round, under-filled GPU).
+static bool size_grids(rem2d_handle* h) {
+    const double smem_kb = h->opt.smem_budget_kb, small_weight = h->opt.small_weight;
+    double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98;
+    double work[N_CLASSES], smem[N_CLASSES];
+    bool fixed[N_CLASSES];
+    for (int k = 0; k < N_CLASSES; ++k) {
+        const int gs = h->cur_gs[k];
+        work[k] = h->cls[k].work; fixed[k] = h->cls[k].n_members == 0; smem[k] = g_classes(k).hot_bytes(gs) + 1024.0;
+        if (g_classes(k).nb <= 8) work[k] *= small_weight;
+        // a group of G lanes is one resident creature: G times the warps for the same residency, and the creature ticks
+        // p(G) times faster (measured tick latencies, profiles/r2_timeline_*.txt)
+        static const double speedup[6] = {1.0, 1.15, 1.5, 1.9, 2.2, 2.5};
+        work[k] *= (double)(1 << gs) / speedup[gs];
+        h->cls[k].episode_grid = 0;
+    }
+    // warps_k = W * work_k with W such that sum_k warps_k * smem_k = budget: every class then needs about the same
+    // number of sequential creature-lifetimes per group times its own tick latency, i.e. the classes finish together.
+    // The register file bounds the resident warps as well (h->max_warps_per_sm, from the occupancy API): a launch whose
+    // CTAs do not fit waits for the CTAs of the classes launched before it to EXIT, which serialises the classes
+    // (measured: the small classes started 400 ms late when 9 warps per SM fit and the grids asked for 9.7).
+    double warp_budget = (double)h->n_sms * h->max_warps_per_sm * 0.97;
+    bool all_fit = true;
+    for (int round = 0; round <= N_CLASSES; ++round) {
+        double denom = 0.0, wsum = 0.0;
+        for (int k = 0; k < N_CLASSES; ++k) if (!fixed[k]) { denom += work[k] * smem[k]; wsum += work[k]; }
+        if (denom <= 0.0) break;
+        const double W = std::max(0.0, std::min(budget / denom, warp_budget / wsum));
+        bool changed = false;
+        for (int k = 0; k < N_CLASSES; ++k) {
+            if (fixed[k]) continue;
+            const int per = 32 >> h->cur_gs[k], need = (h->cls[k].n_members + per - 1) / per;    // one group per creature
+            if ((int)(W * work[k]) >= need) {        // the class fits entirely: fix it and give the rest back
+                h->cls[k].episode_grid = need;
+                budget -= need * smem[k];
+                warp_budget -= need;
+                fixed[k] = true; changed = true;
+            }
+        }
+        if (!changed) {
+            for (int k = 0; k < N_CLASSES; ++k)
+                if (!fixed[k]) { h->cls[k].episode_grid = std::max(1, (int)(W * work[k])); all_fit = false; }
+            break;
+        }
+    }
+    for (int k = 0; k < N_CLASSES; ++k)
+        if (h->cls[k].n_members && h->cls[k].episode_grid < 1) h->cls[k].episode_grid = 1;
+    return all_fit;
+}
+
+// Lanes per creature of every class for the uploaded population, then the grids. Throughput and latency pull in opposite
+// directions: one lane per creature issues the fewest instructions per creature-tick, a group of G lanes ticks a creature
+// up to ~2x faster but spends more issue slots on it (idle lanes in the sweeps, leader sections). Measured on B200
+// (tools/sweep_groups.py): with 65536 creatures the GPU is throughput-bound and G = 1 everywhere is fastest; when the
+// population leaves the GPU under-filled (every creature resident from the start) the run time is one creature lifetime
+// times the tick latency, and wider groups win. So: start from G = 1 and widen the groups of the large classes (up to the
+// class table's value) as long as every creature of every class still has a group from the start. Explicit options
+// ("group_shift", "class_gs_<k>") override the choice.
+static void choose_groups_and_grids(rem2d_handle* h) {
+    bool forced[N_CLASSES];
+    for (int k = 0; k < N_CLASSES; ++k) {
+        const int o = h->opt.group_shift >= 0 ? h->opt.group_shift : h->opt.class_gs[k];
+        forced[k] = o >= 0;
+        h->cur_gs[k] = forced[k] ? std::min(5, o) : 0;
+    }
+    bool all_fit = size_grids(h);
+    if (!all_fit) return;
+    for (bool progress = true; progress;) {
+        progress = false;
+        for (int k = N_CLASSES - 1; k >= 0; --k) {
+            if (forced[k] || !h->cls[k].n_members || h->cur_gs[k] >= g_classes(k).gs) continue;
+            h->cur_gs[k] += 1;
+            if (size_grids(h)) progress = true;
+            else h->cur_gs[k] -= 1;
+        }
+    }
+    size_grids(h);
+}
 
 static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_reset) {
     if (!h || !pop) return REM2D_E_INVALID;
@@ -475,48 +571,13 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         CK(ensure(cs.b_small, 64)); cs.d_n_alive = (int*)cs.b_small.p; cs.d_queue = (int*)cs.b_small.p + 4;
         if (!cs.h_n_alive) CK(cudaMallocHost(&cs.h_n_alive, sizeof(int)));
     }
-    {   // Resident warps of the persistent episode kernels. All classes run concurrently, so the shared memory of the SMs
-        // (227 KB each) is divided among them in proportion to their work (bodies to simulate); a class never gets more
-        // warps than it has batches, and what it cannot use is handed to the others. Without this the largest class
-        // would occupy every SM until its last creature dies and the remaining classes would run after it.
-        const double smem_kb = h->opt.smem_budget_kb, small_weight = h->opt.small_weight;
-        double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98;
-        double work[N_CLASSES], smem[N_CLASSES];
-        bool fixed[N_CLASSES];
+    {   // per-creature cost ~ tick latency of its size: measured ~0.3 ms + 0.085 ms per body for a resident warp; lone bodies
+        // fall asleep after landing and cost almost nothing
         for (int k = 0; k < N_CLASSES; ++k) {
-            work[k] = 0.0; fixed[k] = members[k].empty(); smem[k] = g_classes(k).hot_bytes(class_gs(h, k)) + 1024.0;
-            // per-creature cost ~ tick latency of its size: measured ~0.3 ms + 0.085 ms per body for a resident warp; lone
-            // bodies fall asleep after landing and cost almost nothing
-            for (int c : members[k]) { int nbc = pop->body_off[c + 1] - pop->body_off[c]; work[k] += nbc == 1 ? 1.0 : 3.5 + nbc; }
-            if (g_classes(k).nb <= 8) work[k] *= small_weight;
-            work[k] *= (double)(1 << class_gs(h, k));      // warps per resident creature
-            h->cls[k].episode_grid = 0;
+            h->cls[k].work = 0.0;
+            for (int c : members[k]) { int nbc = pop->body_off[c + 1] - pop->body_off[c]; h->cls[k].work += nbc == 1 ? 1.0 : 3.5 + nbc; }
         }
-        // warps_k = W * work_k with W such that sum_k warps_k * smem_k = budget: every class then needs about the same
-        // number of sequential creature-lifetimes per lane times its own tick latency, i.e. the classes finish together
-        for (int round = 0; round < N_CLASSES; ++round) {
-            double denom = 0.0;
-            for (int k = 0; k < N_CLASSES; ++k) if (!fixed[k]) denom += work[k] * smem[k];
-            if (denom <= 0.0) break;
-            const double W = budget / denom;
-            bool changed = false;
-            for (int k = 0; k < N_CLASSES; ++k) {
-                if (fixed[k]) continue;
-                const int per = 32 >> class_gs(h, k), need = (h->cls[k].n_members + per - 1) / per;    // one group per creature
-                if ((int)(W * work[k]) >= need) {        // the class fits entirely: fix it and give the rest back
-                    h->cls[k].episode_grid = need;
-                    budget -= need * smem[k];
-                    fixed[k] = true; changed = true;
-                }
-            }
-            if (!changed) {
-                for (int k = 0; k < N_CLASSES; ++k)
-                    if (!fixed[k]) h->cls[k].episode_grid = std::max(1, (int)(W * work[k]));
-                break;
-            }
-        }
-        for (int k = 0; k < N_CLASSES; ++k)
-            if (h->cls[k].n_batches && h->cls[k].episode_grid < 1) h->cls[k].episode_grid = 1;
+        choose_groups_and_grids(h);
     }
     {
         const size_t nn = (size_t)std::max(n, 1);
@@ -556,7 +617,7 @@ static int launch_reset(rem2d_handle* h) {
     for (int k = N_CLASSES - 1; k >= 0; --k) {
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
-        g_classes(k).reset(class_gs(h, k), cs.n_batches, cs.stream, cs.d_state, cs.d_lane_creature, h->dpop);
+        g_classes(k).reset(step_gs(h, k), cs.n_batches, cs.stream, cs.d_state, cs.d_lane_creature, h->dpop);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -641,7 +702,7 @@ static int launch_phased(rem2d_handle* h, int max_ticks) {
         if (ticks > max_ticks - cs.done_ticks) ticks = max_ticks - cs.done_ticks;
         cs.done_ticks += ticks;
         int* lc_dst = cs.d_lc_work[cs.lc_next];
-        g_classes(k).step(class_gs(h, k), batches, cs.stream, cs.d_state, ticks, h->d_ter, h->d_consts, h->d_counters);
+        g_classes(k).step(step_gs(h, k), batches, cs.stream, cs.d_state, ticks, h->d_ter, h->d_consts, h->d_counters);
         CK(cudaMemsetAsync(cs.d_n_alive, 0, sizeof(int), cs.stream));
         compact_plan_kernel<<<(cs.cur_lanes + 127) / 128, 128, 0, cs.stream>>>(cs.d_state, cs.lc_cur, cs.cur_lanes, words, max_ticks,
                                                                               h->d_fitness, h->d_ticks, h->d_alive, h->d_status,
@@ -882,7 +943,7 @@ int rem2d_step(rem2d_handle* h, int32_t n_ticks) {
     for (int k = N_CLASSES - 1; k >= 0; --k) {        // most expensive class first
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
-        g_classes(k).step(class_gs(h, k), cs.n_batches, cs.stream, cs.d_state, n_ticks, h->d_ter, h->d_consts, h->d_counters);
+        g_classes(k).step(step_gs(h, k), cs.n_batches, cs.stream, cs.d_state, n_ticks, h->d_ter, h->d_consts, h->d_counters);
         h->launches++;
     }
     CK(cudaGetLastError());

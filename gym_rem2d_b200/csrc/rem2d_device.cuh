@@ -523,6 +523,67 @@ struct Sim {
         setSi(S_NC, nc);
         for (int b = 0; b < nb; ++b) setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) & ~BFL_MOVED);
     }
+    // Group-cooperative FindNewContacts (G > 1): the broad-phase queries of the moved proxies - edge range of the fat AABB,
+    // overlap tests against the edge proxies, "is this pair already a contact" scans of the pool, all of them chains of cold
+    // loads - are strided over the lanes, one body per lane at a time; each body leaves a bit mask of its NEW pairs in its
+    // scratch word, and the leader turns the masks into contacts in Box2D's pair order (ascending edge, then body). New pairs
+    // are rare (a handful per episode), so the leader's part is usually empty. Ends with a group barrier.
+    __device__ void find_new_contacts_group() {
+        if (gs == 0) { find_new_contacts(); return; }
+        const int nc0 = bcast(Si(S_NC));
+        bool has = false, special = false;
+        for (int b = sub; b < nb; b += G) {
+            int w = 0;
+            if (Bi(BF_FLAGS, b) & BFL_MOVED) {
+                double l = floor(((double)B(BF_FLX, b) - 0.25) / (double)ter->step) - 1.0;
+                double u = ceil(((double)B(BF_FHX, b) + 0.25) / (double)ter->step) + 1.0;
+                int il = l < 0.0 ? 0 : (l > (double)(ter->n_edges - 1) ? ter->n_edges : (int)l);
+                int iu = u < 0.0 ? -1 : (u > (double)(ter->n_edges - 1) ? ter->n_edges - 1 : (int)u);
+                if (iu - il >= 24) special = true;            // (a proxy spanning > 24 edges: the leader scans it the slow way)
+                else {
+                    int mask = 0;
+                    for (int e = il; e <= iu; ++e)
+                        if (overlap_edge(e, b) && find_contact(nc0, b, e) < 0) mask |= 1 << (e - il);
+                    if (mask) { w = il | (mask << 8); has = true; }
+                }
+            }
+            AUX(b) = w;
+        }
+        special = group_any(special);
+        has = group_any(has);                 // (also the barrier that publishes the scratch words)
+        if (leader()) {
+            if (special) find_new_contacts();
+            else if (has) {
+                int nc = nc0;
+                int elo = ter->n_edges, ehi = -1;
+                for (int b = 0; b < nb; ++b) {
+                    const int w = AUX(b);
+                    if (!w) continue;
+                    const int il = w & 0xff, m = (int)((unsigned)w >> 8);
+                    if (il < elo) elo = il;
+                    const int top = il + 31 - __clz(m);
+                    if (top > ehi) ehi = top;
+                }
+                for (int e = elo; e <= ehi; ++e)
+                    for (int b = 0; b < nb; ++b) {
+                        const int w = AUX(b);
+                        const int k = e - (w & 0xff);
+                        if (!w || k < 0 || k >= 24 || !(((unsigned)w >> (8 + k)) & 1u)) continue;
+                        if (nc == L.nc) { setSi(S_STATUS, Si(S_STATUS) | ST_POOL_OVERFLOW); continue; }
+                        setCi(CF_KEY, nc, b | (e << 8) | (CK_ENABLED << 16));
+                        C(CF_TOI, nc) = 1.0f;
+                        C(CF_P0N, nc) = 0.0f; C(CF_P0T, nc) = 0.0f; C(CF_P1N, nc) = 0.0f; C(CF_P1T, nc) = 0.0f;
+                        ++nc;
+                        set_awake(b, true);
+                    }
+                setSi(S_NC, nc);
+            }
+        }
+        gsync();
+        if (!special)
+            for (int b = sub; b < nb; b += G) setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) & ~BFL_MOVED);
+        gsync();
+    }
     __device__ void destroy_contact(int i) {
         int nc = Si(S_NC);
         int key = Ci(CF_KEY, i);
@@ -1224,8 +1285,19 @@ struct Sim {
                     if (h2 < hi) hi = h2;
                 }
             }
+            // lane: constraint idx lives in hot column (idx & (G-1)), so the lane with that index reads and writes its fields
+            // without shared-memory bank conflicts; it is preferred when it is free in the earliest possible slot or the next
+            // one, otherwise any free lane of the earliest slot with one takes the constraint
             int t = lo, lane_k = -1;
-            while (t <= hi) {
+            {
+                const int pref = idx & (G - 1);
+                int t2 = lo;
+                for (int tries = 0; tries < 2 && t2 <= hi; ++tries) {
+                    if (SCH(t2 & 31, pref) == 0) { t = t2; lane_k = pref; break; }
+                    ++t2; if ((t2 & 31) == P) t2 = (t2 & ~31) + 32;
+                }
+            }
+            while (lane_k < 0 && t <= hi) {
                 const int pslot = t & 31;
                 for (int kk = 0; kk < G; ++kk)
                     if (SCH(pslot, kk) == 0) { lane_k = kk; break; }
@@ -1442,8 +1514,7 @@ struct Sim {
             for (int b = sub; b < nb; b += G) set_awake(b, false);
         for (int b = sub; b < nb; b += G) synchronize_fixtures(b);      // (independent per body: any order)
         gsync();
-        if (leader()) find_new_contacts();
-        gsync();
+        find_new_contacts_group();
     }
 
     // ---- continuous collision: b2TimeOfImpact / b2Distance with proxy A = terrain edge (identity frame)
@@ -1859,7 +1930,8 @@ struct Sim {
         const int newfix = bcast(Si(S_NEWFIX));
         gsync();
         if (newfix) {
-            if (leader()) { find_new_contacts(); setSi(S_NEWFIX, 0); }
+            find_new_contacts_group();
+            if (leader()) setSi(S_NEWFIX, 0);
             gsync();
         }
         float dtRatio = S(S_INVDT0) * dt;

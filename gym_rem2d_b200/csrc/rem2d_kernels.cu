@@ -75,7 +75,10 @@ void rem2d_launch_step(const Layout& L, int gs, int n_batches, cudaStream_t st, 
 // the long-lived creatures bound the makespan, and a 32-lane schedule ticks a large creature several times faster than
 // the throughput-oriented groups of the queue mode.
 // Dynamic shared memory: make_hot_layout(L, gs).rows * 128 B.
-__global__ void __launch_bounds__(32, 1) episode_kernel(const __grid_constant__ Layout L, int gs, int mode, float* slots,
+#ifndef REM2D_MIN_BLOCKS
+#define REM2D_MIN_BLOCKS 16        // register cap: 65536 / (32 * 16) = 128 registers per thread (no spills, see Makefile / DESIGN.md)
+#endif
+__global__ void __launch_bounds__(32, REM2D_MIN_BLOCKS) episode_kernel(const __grid_constant__ Layout L, int gs, int mode, float* slots,
                                                         const int* __restrict__ order, int n_order, int* queue, DevPop p,
                                                         const Terrain* __restrict__ ter, const Consts* __restrict__ k, int max_ticks,
                                                         double* fitness, int* ticks, int* alive, int* status,
@@ -194,6 +197,12 @@ void rem2d_launch_episode(const Layout& L, int gs, int grid, cudaStream_t st, fl
     episode_kernel<<<grid, 32, make_hot_layout(L, gs).rows * 128, st>>>(L, gs, 0, slots, order, n_order, queue, p, ter, k, max_ticks, fitness,
                                                                          ticks, alive, status, counters, park, park_state, park_creature,
                                                                          park_count, 0, 0);
+}
+// resident CTAs (= warps) of the episode kernel per SM for a given dynamic shared-memory size: registers AND shared memory
+int rem2d_episode_blocks_per_sm(int dyn_smem_bytes) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, episode_kernel, 32, (size_t)dyn_smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 void rem2d_launch_tail(const Layout& L, int gs, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked,
                        const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,

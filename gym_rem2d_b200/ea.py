@@ -10,7 +10,13 @@ generations / on every generation with a positive best (REM2D_main.py:192-195,31
 reference's (Experiments/configuration_maker.py:10-63, 0.cfg).
 
 Host-side expansion (mutate -> genome.create -> flatten) is Python and dominates a generation at large population
-sizes, so it can be spread over a process pool; evaluation itself is one ``rem2d_evaluate`` call.
+sizes, so variation AND expansion run in a PERSISTENT process pool (created in ``__init__``, i.e. before
+the CUDA context exists in this process; ``forkserver`` start method, so no worker ever inherits driver state): the parent
+only draws the tournament winners and ships chunks of parents, the workers deep-copy, mutate and flatten them and return
+(offspring, table). Evaluation itself is one ``rem2d_evaluate`` call per generation, or - under ``torch.distributed`` -
+one call per rank on its shard of the table plus one all_gather of the fitness vector (distributed.evaluate_sharded).
+Checkpoints are written under the reference's class paths (refpickle.py) and numbered by ABSOLUTE generation, so a resumed
+run never overwrites or re-reads an older population.
 """
 import configparser
 import copy
@@ -71,8 +77,21 @@ def _expand_chunk(args):
     return flatten_population(inds, depth)
 
 
+def _vary_chunk(args):
+    """Worker: variation + expansion of one chunk of selected parents (REM2D_main.py:283-290 + evaluate's genome.create).
+    Parents arrive pickled (= the deep copy of ``toolbox.clone``); every chunk is seeded so that a run is reproducible
+    for a fixed number of workers."""
+    parents, depth, mmr, mr, sigma, seed = args
+    random.seed(seed)
+    np.random.seed(seed % (2 ** 32))
+    for o in parents:
+        Individual.mutate(mmr, mr, sigma, o)
+        o.fitness = 0
+    return parents, flatten_population(parents, depth)
+
+
 class run2D:
-    def __init__(self, config, dir, env=None, workers=0):
+    def __init__(self, config, dir, env=None, workers=0, distributed=False):
         self.config = config
         self.start_time = time.time()
         self.fitnessData = FitnessData()
@@ -90,73 +109,128 @@ class run2D:
         self.moduleList = get_module_list()
         self.env = env
         self.workers = workers
+        self.distributed = distributed       # evaluate this rank's shard and all_gather (torch.distributed must be initialised)
         self.generation_log = []
+        self.generation_offset = 0           # generations already done by the run this one resumes
+        # persistent workers, started BEFORE any CUDA work of this process (the engine is created lazily, later)
+        self.pool = mp.get_context("forkserver").Pool(workers) if workers > 1 else None
 
-    # -- batched replacement of toolbox.map(toolbox.evaluate, individuals)
-    def evaluate_batch(self, individuals):
+    def close(self):
+        if self.pool is not None:
+            self.pool.terminate()
+            self.pool = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chunks(self, items):
+        step = max(1, (len(items) + max(self.workers, 1) * 4 - 1) // (max(self.workers, 1) * 4))
+        return [items[i:i + step] for i in range(0, len(items), step)]
+
+    def _ensure_env(self):
         if self.env is None:
             from .env import BatchedModular2D
-            self.env = BatchedModular2D()
+            device = 0
+            if self.distributed:
+                device = int(os.environ.get("LOCAL_RANK", "0"))
+            self.env = BatchedModular2D(device=device)
+        return self.env
+
+    # -- batched replacement of toolbox.map(toolbox.evaluate, individuals)
+    def evaluate_table(self, table):
+        env = self._ensure_env()
+        env.seed(K.TERRAIN_SEED)
+        if self.distributed:
+            from . import distributed as rdist
+            fit, steps = rdist.evaluate_sharded(table, env.engine, self.EVALUATION_STEPS)
+            return [float(f) for f in fit], steps
+        fit = env.evaluate(table=table, steps=self.EVALUATION_STEPS)
+        return [float(f) for f in fit], int(env.last_ticks.sum())
+
+    def evaluate_batch(self, individuals):
         t0 = time.perf_counter()
-        if self.workers > 1 and len(individuals) >= 4 * self.workers:
-            step = (len(individuals) + self.workers - 1) // self.workers
-            chunks = [(individuals[i:i + step], self.TREE_DEPTH) for i in range(0, len(individuals), step)]
-            with mp.get_context("fork").Pool(self.workers) as pool:
-                table = concat(pool.map(_expand_chunk, chunks))
+        if self.pool is not None and len(individuals) >= 4 * self.workers:
+            table = concat(self.pool.map(_expand_chunk, [(c, self.TREE_DEPTH) for c in self._chunks(individuals)]))
         else:
             table = flatten_population(individuals, self.TREE_DEPTH)
         t1 = time.perf_counter()
-        self.env.seed(K.TERRAIN_SEED)
-        fit = self.env.evaluate(table=table, steps=self.EVALUATION_STEPS)
+        fit, steps = self.evaluate_table(table)
         t2 = time.perf_counter()
-        self.last_timing = {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "creature_steps": int(self.env.last_ticks.sum())}
-        return [float(f) for f in fit]
+        self.last_timing = {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "creature_steps": steps}
+        return fit
+
+    def vary_and_expand(self, parents):
+        """clone + mutate + expand: in the workers when there is a pool, else here."""
+        if self.pool is not None and len(parents) >= 4 * self.workers:
+            jobs = [(c, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, random.getrandbits(48))
+                    for c in self._chunks(parents)]
+            parts = self.pool.map(_vary_chunk, jobs)
+            return [o for p, _ in parts for o in p], concat([t for _, t in parts])
+        offspring = [copy.deepcopy(o) for o in parents]
+        for o in offspring:
+            Individual.mutate(self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, o)
+            o.fitness = 0
+        return offspring, flatten_population(offspring, self.TREE_DEPTH)
 
     def run(self, config=None, continue_progression=False, n_generations=None):
+        from . import refpickle
         population = None
         if continue_progression:
-            self.fitnessData = pickle.load(open(self.SAVE_FILE_DIRECTORY, "rb"))
-            last = max(int(f[len("s_pop"):]) for f in os.listdir(os.path.dirname(self.SAVE_FILE_DIRECTORY)) if f.startswith("s_pop"))
-            population = pickle.load(open(self.SAVE_FILE_DIRECTORY + self.POPULATION_FILE + str(last), "rb"))
+            self.fitnessData = refpickle.load(self.SAVE_FILE_DIRECTORY)
+            d = os.path.dirname(self.SAVE_FILE_DIRECTORY)
+            last = max(int(f[len("s_pop"):]) for f in os.listdir(d) if f.startswith("s_pop") and f[len("s_pop"):].isdigit())
+            population = refpickle.load(self.SAVE_FILE_DIRECTORY + self.POPULATION_FILE + str(last))
+            # s_ may hold generations after the newest population checkpoint: the run continues from the population,
+            # so the fitness history is cut back to it (absolute generation = index of the checkpoint + 1)
+            self.generation_offset = last + 1
+            for k in ("p_0", "p_25", "p_50", "p_75", "p_100", "avg"):
+                setattr(self.fitnessData, k, list(getattr(self.fitnessData, k))[:self.generation_offset])
         return self.run_deap(config or self.config, population=population, n_generations=n_generations)
 
+    def _checkpoint(self, population, g):
+        from . import refpickle
+        refpickle.dump(self.fitnessData, self.SAVE_FILE_DIRECTORY)
+        refpickle.dump(population, self.SAVE_FILE_DIRECTORY + self.POPULATION_FILE + str(g))
+
     def run_deap(self, config, population=None, useTQDM=False, n_generations=None):
+        from . import refpickle
         N_GENERATIONS = 1 + int(int(config['ea']['n_evaluations']) / self.POPULATION_SIZE)
         N_GENERATIONS -= len(self.fitnessData.avg)
         if n_generations is not None:
             N_GENERATIONS = n_generations
+        rank0 = (not self.distributed) or int(os.environ.get("RANK", "0")) == 0
         if population is None:
             population = [Individual.random(self.moduleList, self.config) for _ in range(self.POPULATION_SIZE)]
             for ind, fit in zip(population, self.evaluate_batch(population)):
                 ind.fitness = fit
-        gen = 0
         for i in range(N_GENERATIONS):
-            gen += 1
+            g = self.generation_offset + i                     # absolute generation index (file suffix)
             t0 = time.perf_counter()
-            offspring = selTournament(population, len(population), tournsize=4)
-            offspring = [copy.deepcopy(o) for o in offspring]
-            for o in offspring:
-                Individual.mutate(self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, o)
-                o.fitness = 0
-            fitness_values = self.evaluate_batch(offspring)
+            parents = selTournament(population, len(population), tournsize=4)
+            offspring, table = self.vary_and_expand(parents)
+            t1 = time.perf_counter()
+            fitness_values, steps = self.evaluate_table(table)
+            t2 = time.perf_counter()
             for ind, fit in zip(offspring, fitness_values):
                 ind.fitness = fit
             population = offspring                                   # no elitism, like the reference
             self.EVALUATION_NR += len(population)
-            self.fitnessData.addFitnessData(fitness_values, gen)
-            self.generation_log.append({"generation": i + 1, "min": float(np.min(fitness_values)), "max": float(np.max(fitness_values)),
+            self.fitnessData.addFitnessData(fitness_values, g + 1)
+            self.generation_log.append({"generation": g + 1, "min": float(np.min(fitness_values)), "max": float(np.max(fitness_values)),
                                         "mean": float(np.mean(fitness_values)), "seconds": time.perf_counter() - t0,
-                                        **self.last_timing})
-            if self.SAVEDATA:
-                if i % self.CHECKPOINT_FREQUENCY == 0 or i == N_GENERATIONS:
-                    self.fitnessData.save(self.SAVE_FILE_DIRECTORY)
-                    pickle.dump(population, open(self.SAVE_FILE_DIRECTORY + self.POPULATION_FILE + str(i), "wb"))
+                                        "expand_s": t1 - t0, "evaluate_s": t2 - t1, "creature_steps": steps})
+            if self.SAVEDATA and rank0:
+                if g % self.CHECKPOINT_FREQUENCY == 0 or i == N_GENERATIONS - 1:     # the last generation is always saved
+                    self._checkpoint(population, g)
                 bestfit, best = 0.0, None
                 for o in offspring:
                     if o.fitness > bestfit:
                         bestfit, best = o.fitness, o
                 if best is not None:
-                    pickle.dump(best, open(self.SAVE_FILE_DIRECTORY + self.BEST_INDIVIDUAL_FILE + str(i), "wb"))
+                    refpickle.dump(best, self.SAVE_FILE_DIRECTORY + self.BEST_INDIVIDUAL_FILE + str(g))
             if time.time() - self.start_time > int(config.get("ea", "wallclock_time_limit", fallback=str(2 ** 62))):
                 break
         self.population = population

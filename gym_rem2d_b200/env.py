@@ -109,8 +109,21 @@ class Modular2D:
         reward, done = self._batched.step(1)
         return 0, float(reward[0]), bool(done[0]), 0
 
-    def render(self, mode='human'):
-        raise NotImplementedError("rendering (pyglet viewer, Modular2DEnv.py:655-768) is out of scope of this path")
+    def render(self, mode='human', path=None):
+        """Headless replacement of the pyglet viewer (Modular2DEnv.py:655-738): rasterises the current state of the creature.
+        ``rgb_array`` returns the image; ``human`` writes it as a PNG (``path`` or ./rem2d_frame_<tick>.png) and returns
+        the file name - there is no window on a GPU box."""
+        from . import render as _render
+        if self.tree_morphology is None:
+            raise Exception("no tree_morphology")
+        b = self._batched
+        st = b.engine.read_state()
+        img = _render.render_creature(b.table, 0, st["pose"], b.terrain_y, wod=float(st["wod"][0]))
+        if mode == 'rgb_array':
+            return img
+        path = path or "rem2d_frame_%05d.png" % int(st["ticks"][0])
+        _render.write_png(path, img)
+        return path
 
     def close(self):
         self._batched.close()

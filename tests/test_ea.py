@@ -43,14 +43,25 @@ def test_generations_checkpoints_and_formats(tmp_path):
     assert len(run.fitnessData.avg) == 4 and run.fitnessData.p_100[-1] >= run.fitnessData.p_0[-1]
     files = sorted(os.listdir(tmp_path))
     assert "s_" in files and "s_pop0" in files and "s_pop2" in files and any(f.startswith("s_elite") for f in files)
-    saved = pickle.load(open(tmp_path / "s_pop2", "rb"))
+    from gym_rem2d_b200 import refpickle
+    assert "s_pop3" in files                                    # the last generation is always checkpointed
+    saved = refpickle.load(tmp_path / "s_pop2")
     assert len(saved) == 24 and saved[0].genome.create(saved[0].tree_depth).getNodes()
-    fd = pickle.load(open(tmp_path / "s_", "rb"))
-    assert isinstance(fd, ea.FitnessData) and len(fd.avg) >= 3
-    # resume
+    assert b"REM2D_main" in open(tmp_path / "s_pop2", "rb").read()      # written under the reference's class paths
+    fd = refpickle.load(tmp_path / "s_")
+    assert isinstance(fd, ea.FitnessData) and len(fd.avg) == 4
+    # resume: continues from the newest population, absolute generation numbers, history cut to the checkpoint
     run2 = ea.run2D(cfg, str(tmp_path), env=StubEnv())
-    pop2 = run2.run(cfg, continue_progression=True, n_generations=1)
-    assert len(pop2) == 24 and len(run2.fitnessData.avg) == len(fd.avg) + 1
+    pop2 = run2.run(cfg, continue_progression=True, n_generations=3)
+    assert len(pop2) == 24 and len(run2.fitnessData.avg) == 7
+    files = sorted(os.listdir(tmp_path))
+    assert "s_pop4" in files and "s_pop6" in files and "s_pop5" not in files
+    # resume a second time: picks s_pop6 (the newest), never an older file; nothing is overwritten out of order
+    run3 = ea.run2D(cfg, str(tmp_path), env=StubEnv())
+    run3.run(cfg, continue_progression=True, n_generations=2)
+    assert run3.generation_offset == 7 and len(run3.fitnessData.avg) == 9
+    assert [g["generation"] for g in run3.generation_log] == [8, 9]
+    assert "s_pop8" in os.listdir(tmp_path)
     # selection pressure with the body-count fitness: creatures grow
     assert run.generation_log[-1]["mean"] >= run.generation_log[0]["mean"] - 1.0
 
@@ -62,6 +73,14 @@ def test_parallel_expansion_equals_serial():
     a = ea.run2D(cfg, "", env=StubEnv(), workers=0)
     b = ea.run2D(cfg, "", env=StubEnv(), workers=4)
     assert a.evaluate_batch(inds) == b.evaluate_batch(inds)
+    # variation in the persistent workers: same population size, valid offspring, tables consistent with the offspring
+    random.seed(5)
+    off, table = b.vary_and_expand(inds)
+    assert len(off) == 40 and table.n_creatures == 40
+    from gym_rem2d_b200.flatten import flatten_population
+    assert np.array_equal(flatten_population(off, b.TREE_DEPTH).x0, table.x0)
+    assert b.pool is not None
+    b.close()
 
 
 @pytest.mark.gpu

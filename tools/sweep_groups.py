@@ -20,7 +20,8 @@ for cfg in configs:
     os.environ["REM2D_CLASS_GS"] = cfg.split(";")[0]
     for k_, v_ in env.items():
         os.environ[k_] = v_
-    g = Engine(device=0)
+    lib = env.pop("LIB", None)
+    g = Engine(device=0, lib_path=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gym_rem2d_b200", "csrc", lib) if lib else None)
     g.set_terrain(ys, K.TERRAIN_STEP)
     g.upload(pop)
     ms = []

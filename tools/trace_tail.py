@@ -9,10 +9,13 @@ from gym_rem2d_b200.population import random_population
 
 pop = random_population(65536, ("lsystem",), seed=2, cache_dir="/tmp/rem2d_cache")
 xs, ys = terrain.generate_terrain()
-os.environ["REM2D_TRACE"] = "1"
-for pt in [int(a) for a in sys.argv[1:]] or [256]:
-    os.environ["REM2D_PARK_TICKS"] = str(pt)
+for arg in sys.argv[1:] or ["256"]:
+    pt, tgs = (arg.split(":") + ["5"])[:2]
+    pt = int(pt)
     e = Engine(device=0)
+    e.set_option("trace", 1); e.set_option("park_ticks", pt); e.set_option("tail_group_shift", int(tgs))
+    if pt < 200:
+        e.set_option("park_cap", 0.25)
     e.set_terrain(ys, K.TERRAIN_STEP)
     e.upload(pop)
     e.run_episodes(10000)
@@ -28,7 +31,7 @@ for pt in [int(a) for a in sys.argv[1:]] or [256]:
             a = buf[: w * 2048].reshape(w, 1024, 2)
             v = a[:, :, 0][a[:, :, 0] > 0]
             t0 = int(v.min()) if t0 is None else min(t0, int(v.min()))
-    print("park at %d ticks: run %.0f ms" % (pt, ms))
+    print("park at %d ticks, tail group shift %s: run %.0f ms" % (pt, tgs, ms))
     allr = []
     for k in range(9):
         n = e.lib.rem2d_debug_tail_trace(e.h, k, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
