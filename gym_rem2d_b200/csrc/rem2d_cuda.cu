@@ -112,6 +112,7 @@ __global__ void fp32_issue_kernel(float* out, int iters, float b, float c) {
 // ------------------------------------------------------------------ handle
 // Device buffers are grow-only and reused across uploads: re-allocating ~1 GB of state blocks on every rem2d_evaluate
 // call cost ~0.4 s per generation.
+#define N_COUNTER_WORDS (REM2D_N_COUNTERS + 12 * 16)      // work counters + phase cycles of diagnostic builds (REM2D_PHASE_TIMING)
 struct Buf { void* p = nullptr; size_t cap = 0; };
 static cudaError_t ensure(Buf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return cudaSuccess;
@@ -128,6 +129,10 @@ struct ClassState {
     int n_batches = 0;
     int n_members = 0;                  // creatures of this class (lane_creature[0..n_members) are real)
     int episode_grid = 0;               // resident warps of the persistent episode kernel
+    int grid2 = 0, gs2 = 0;             // second, wider-grouped launch for the creatures that do not fit in the first round
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t done2 = nullptr;
+    ParkPolicy park{};
     double work = 0.0;                  // sum of the per-creature cost estimates (grid sizing)
     float* d_state = nullptr;
     int* d_lane_creature = nullptr;
@@ -157,11 +162,15 @@ struct Options {
     int warp_mode_max = -1;      // largest population that runs one warp per creature from tick 0 (-1: 48 per SM)
     int park_ticks = -1;         // park threshold of the queue mode (-1: automatic, 0: never park)
     double park_cap = -1.0;      // fraction of a class that may be parked (-1: automatic)
+    int park_late_ticks = -1;    // park threshold of creatures pulled after the first round (-1: same as park_ticks)
     double smem_budget_kb = 227.0, small_weight = 1.0;
     int min_class = 0;
     int group_shift = -1;        // log2 lanes per creature in the queue / step kernels (-1: per class default)
     int class_gs[N_CLASSES] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per capacity class ("class_gs_<k>", -1: default)
-    int tail_group_shift = 5;    // log2 lanes per creature of the tail launches
+    int tail_group_shift = 3;    // log2 lanes per creature of the tail launches (measured: 8 lanes tick a large creature as fast as 32)
+    int second_group_shift = -1; // log2 lanes per creature of a second launch for the creatures a large class cannot seat in its first
+                                 // round (-1: off = refill the first launch's lanes). Measured and rejected as default: the GPU is
+                                 // still throughput-bound when the first round ends, wide groups only add issue load (+25 % run time)
     int trace = 0;
     int phased = 0;              // tick phases with survivor compaction instead of the persistent queue kernel
 };
@@ -186,7 +195,8 @@ struct rem2d_handle {
     bool state_valid = false;           // per-creature state blocks hold a consistent snapshot (reset/step path)
     bool results_valid = false;         // d_fitness/d_ticks/... were written by the episode kernel
     int n_sms = 0;
-    int max_warps_per_sm = 16;          // resident warps of the episode kernel per SM by registers (occupancy API)
+    int max_warps_per_sm[2] = {8, 16};  // resident warps of the two episode kernel images per SM by registers (occupancy API)
+    int image = 0;                      // kernel image of the current population (0: 200 registers, 1: 128 registers)
     int n_edges = 0;
     // population
     int n_creatures = 0, n_bodies = 0, n_joints = 0;
@@ -235,11 +245,13 @@ static bool set_option(Options& o, const char* name, double v) {
     if (n == "warp_mode_max") o.warp_mode_max = (int)v;
     else if (n == "park_ticks") o.park_ticks = (int)v;
     else if (n == "park_cap") o.park_cap = v;
+    else if (n == "park_late_ticks") o.park_late_ticks = (int)v;
     else if (n == "smem_budget_kb") o.smem_budget_kb = v;
     else if (n == "small_weight") o.small_weight = v;
     else if (n == "min_class") o.min_class = std::max(0, std::min(N_CLASSES - 1, (int)v));
     else if (n == "group_shift") o.group_shift = (int)v;
     else if (n == "tail_group_shift") o.tail_group_shift = std::max(0, std::min(5, (int)v));
+    else if (n == "second_group_shift") o.second_group_shift = std::max(-1, std::min(5, (int)v));
     else if (n == "trace") o.trace = (int)v;
     else if (n == "phased") o.phased = (int)v;
     else if (n.rfind("class_gs_", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] < '0' + N_CLASSES) o.class_gs[n[9] - '0'] = (int)v;
@@ -247,8 +259,8 @@ static bool set_option(Options& o, const char* name, double v) {
     return true;
 }
 static void options_from_env(Options& o) {
-    static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "smem_budget_kb", "small_weight", "min_class",
-                                  "group_shift", "tail_group_shift", "trace"};
+    static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "park_late_ticks", "smem_budget_kb", "small_weight", "min_class",
+                                  "group_shift", "tail_group_shift", "second_group_shift", "trace"};
     for (const char* n : names) {
         std::string env = "REM2D_";
         for (const char* q = n; *q; ++q) env += (char)toupper(*q);
@@ -322,12 +334,14 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
     auto fail = [&](const char* what, cudaError_t err) { g_create_err = std::string(what) + ": " + cudaGetErrorString(err); rem2d_destroy(h); return REM2D_E_CUDA; };
     if ((e = cudaMalloc(&h->d_ter, sizeof(Terrain))) != cudaSuccess) return fail("cudaMalloc terrain", e);
     if ((e = cudaMalloc(&h->d_consts, sizeof(Consts))) != cudaSuccess) return fail("cudaMalloc consts", e);
-    if ((e = cudaMalloc(&h->d_counters, sizeof(unsigned long long) * REM2D_N_COUNTERS)) != cudaSuccess) return fail("cudaMalloc counters", e);
-    if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS)) != cudaSuccess) return fail("cudaMemset counters", e);
+    if ((e = cudaMalloc(&h->d_counters, sizeof(unsigned long long) * N_COUNTER_WORDS)) != cudaSuccess) return fail("cudaMalloc counters", e);
+    if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * N_COUNTER_WORDS)) != cudaSuccess) return fail("cudaMemset counters", e);
     Consts k = make_consts(cfg);
     if ((e = cudaMemcpy(h->d_consts, &k, sizeof(k), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy consts", e);
     for (auto& c : h->cls) {
         if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&c.done2, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
         if ((e = cudaEventCreate(&c.t_begin)) != cudaSuccess || (e = cudaEventCreate(&c.t_end)) != cudaSuccess) return fail("cudaEventCreate", e);
     }
@@ -346,7 +360,7 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
         for (int q = 0; q < N_CLASSES; ++q)
             for (int gs = 0; gs <= 5; ++gs) max_hot = std::max(max_hot, g_classes(q).hot_bytes(gs));
         if ((e = rem2d_set_kernel_attributes(max_hot, carve)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
-        h->max_warps_per_sm = std::max(1, rem2d_episode_blocks_per_sm(1024));
+        for (int im = 0; im < 2; ++im) h->max_warps_per_sm[im] = std::max(1, rem2d_episode_blocks_per_sm(im, 1024));
     }
     *out = h;
     return REM2D_OK;
@@ -366,7 +380,9 @@ int rem2d_destroy(rem2d_handle* h) {
     release_buffers(h);
     for (auto& c : h->cls) {
         if (c.stream) cudaStreamDestroy(c.stream);
+        if (c.stream2) cudaStreamDestroy(c.stream2);
         if (c.done) cudaEventDestroy(c.done);
+        if (c.done2) cudaEventDestroy(c.done2);
         if (c.t_begin) cudaEventDestroy(c.t_begin);
         if (c.t_end) cudaEventDestroy(c.t_end);
     }
@@ -440,7 +456,7 @@ static bool size_grids(rem2d_handle* h) {
     // The register file bounds the resident warps as well (h->max_warps_per_sm, from the occupancy API): a launch whose
     // CTAs do not fit waits for the CTAs of the classes launched before it to EXIT, which serialises the classes
     // (measured: the small classes started 400 ms late when 9 warps per SM fit and the grids asked for 9.7).
-    double warp_budget = (double)h->n_sms * h->max_warps_per_sm * 0.97;
+    double warp_budget = (double)h->n_sms * h->max_warps_per_sm[h->image] * 0.97;
     bool all_fit = true;
     for (int round = 0; round <= N_CLASSES; ++round) {
         double denom = 0.0, wsum = 0.0;
@@ -484,8 +500,28 @@ static void choose_groups_and_grids(rem2d_handle* h) {
         forced[k] = o >= 0;
         h->cur_gs[k] = forced[k] ? std::min(5, o) : 0;
     }
+    // under-filled GPU <=> everything fits with one lane per creature in the 128-register image: then widen (below)
+    h->image = 1;
     bool all_fit = size_grids(h);
-    if (!all_fit) return;
+    if (!all_fit) { h->image = 0; size_grids(h); }
+    for (int k = 0; k < N_CLASSES; ++k) { h->cls[k].grid2 = 0; h->cls[k].gs2 = 0; }
+    if (!all_fit) {
+        // Throughput-bound population: one lane per creature in the first round. The creatures of the LARGE classes that do
+        // not get a lane then are not run by refilled lanes - one more lap at the bulk tick latency (2.2 ms for 17-21 bodies)
+        // that would start when the first lap ends and push the long-lived creatures among them to the end of the run - but
+        // by a second launch with wide groups (2-4x lower tick latency) whose CTAs become resident as the first launch's
+        // warps exit: by then the small classes are draining and issue slots are free.
+        const int gs2 = h->opt.second_group_shift;
+        for (int k = 0; k < N_CLASSES && gs2 >= 0; ++k) {
+            ClassState& cs = h->cls[k];
+            const int per1 = 32 >> h->cur_gs[k];
+            const int left = cs.n_members - cs.episode_grid * per1;
+            if (left <= 0 || g_classes(k).nb < 12 || forced[k]) continue;
+            cs.gs2 = std::max(gs2, h->cur_gs[k]);
+            cs.grid2 = (left + (32 >> cs.gs2) - 1) / (32 >> cs.gs2);
+        }
+        return;
+    }
     for (bool progress = true; progress;) {
         progress = false;
         for (int k = N_CLASSES - 1; k >= 0; --k) {
@@ -560,7 +596,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         cs.lane_creature.assign((size_t)cs.n_batches * 32, -1);
         for (size_t i = 0; i < m.size(); ++i) { cs.lane_creature[i] = m[i]; h->creature_lane[m[i]] = (int)i; }
         const size_t lane_bytes = cs.lane_creature.size() * sizeof(int);
-        const size_t state_bytes = (size_t)cs.n_batches * g_classes(k).words * 32 * sizeof(float);
+        const size_t state_bytes = (size_t)(cs.n_batches + 2) * g_classes(k).words * 32 * sizeof(float);   // (+2: second launch's columns)
         CK(ensure(cs.b_lc, lane_bytes)); cs.d_lane_creature = (int*)cs.b_lc.p;
         CK(cudaMemcpy(cs.d_lane_creature, cs.lane_creature.data(), cs.lane_creature.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(ensure(cs.b_state, state_bytes)); cs.d_state = (float*)cs.b_state.p;
@@ -597,11 +633,14 @@ extern "C" int rem2d_upload(rem2d_handle* h, const rem2d_population* pop) { retu
 // fork the class streams off the user stream / join them back
 static int fork_streams(rem2d_handle* h) {
     CK(cudaEventRecord(h->ev_fork, h->user_stream));
-    for (auto& c : h->cls) if (c.n_batches) CK(cudaStreamWaitEvent(c.stream, h->ev_fork, 0));
+    for (auto& c : h->cls) if (c.n_batches) { CK(cudaStreamWaitEvent(c.stream, h->ev_fork, 0)); CK(cudaStreamWaitEvent(c.stream2, h->ev_fork, 0)); }
     return REM2D_OK;
 }
 static int join_streams(rem2d_handle* h) {
-    for (auto& c : h->cls) if (c.n_batches) { CK(cudaEventRecord(c.done, c.stream)); CK(cudaStreamWaitEvent(h->user_stream, c.done, 0)); }
+    for (auto& c : h->cls) if (c.n_batches) {
+        CK(cudaEventRecord(c.done, c.stream)); CK(cudaStreamWaitEvent(h->user_stream, c.done, 0));
+        CK(cudaEventRecord(c.done2, c.stream2)); CK(cudaStreamWaitEvent(h->user_stream, c.done2, 0));
+    }
     return REM2D_OK;
 }
 
@@ -623,7 +662,7 @@ static int launch_reset(rem2d_handle* h) {
     CK(cudaGetLastError());
     rc = join_streams(h);
     if (rc) return rc;
-    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * N_COUNTER_WORDS, h->user_stream));
     h->state_valid = true; h->results_valid = false;
     return REM2D_OK;
 }
@@ -662,9 +701,9 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
             int* d_queue = d_order + redo[k].size();
             CK(cudaMemcpyAsync(d_order, redo[k].data(), sizeof(int) * redo[k].size(), cudaMemcpyHostToDevice, h->user_stream));
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
-            g_classes(k).episode(gs, grid, h->user_stream, (float*)cs.b_redo_slots.p, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter,
+            g_classes(k).episode(h->image, gs, grid, h->user_stream, (float*)cs.b_redo_slots.p, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter,
                                  h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                                 ParkPolicy{0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr);
+                                 ParkPolicy{0, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr, 1);
             h->launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->user_stream));      // redo[] (pageable source of the copy) goes out of scope
@@ -772,11 +811,13 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
             const int per = 32 >> class_gs(h, k);
             if (h->cls[k].n_batches && h->cls[k].episode_grid * per < h->cls[k].n_members) single_round = false;
         }
-        if (single_round) { park_ticks = 160; cap_frac = 0.25; }
+        bool second = false;
+        for (int k = 0; k < N_CLASSES; ++k) second |= h->cls[k].grid2 > 0;
+        if (single_round || second) { park_ticks = 160; cap_frac = 0.25; }
     }
     if (h->opt.park_ticks >= 0) park_ticks = h->opt.park_ticks;
     if (h->opt.park_cap >= 0.0) cap_frac = h->opt.park_cap;
-    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * REM2D_N_COUNTERS, h->user_stream));
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * N_COUNTER_WORDS, h->user_stream));
     CK(cudaEventRecord(h->ev_start, h->user_stream));
     int rc = fork_streams(h);
     if (rc) return rc;
@@ -794,9 +835,9 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
         CK(cudaEventRecord(cs.t_begin, cs.stream));
         if (warp_mode) {      // queue mode with a whole warp per creature and one warp for every creature
-            g_classes(k).episode(5, cs.n_members, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
+            g_classes(k).episode(1, 5, cs.n_members, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
                                  h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                                 ParkPolicy{0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr);
+                                 ParkPolicy{0, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr, 1);
             CK(cudaEventRecord(cs.t_end, cs.stream));
             h->launches++;
             continue;
@@ -806,6 +847,10 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         ParkPolicy park;
         park.ticks = park_ticks < max_ticks ? park_ticks : 0;
         park.cap = std::min(cs.n_members, std::max(32, std::min((int)(h->n_sms * 64 * cap_frac), (int)(cs.n_members * cap_frac))));
+        // late starters (pulled when a lane of the first round frees up): park right after the wall of death has passed the
+        // start pad (tick 126), so that the long-lived ones among them continue at the tail launches' tick latency
+        park.late_from = cs.episode_grid * (32 >> class_gs(h, k));
+        park.late_ticks = h->opt.park_late_ticks >= 0 ? std::min(h->opt.park_late_ticks, park.ticks) : park.ticks;
         park.trace = nullptr; park.tail_trace = nullptr;
         if (trace) {
             const size_t tb = (size_t)std::max(cs.n_members, 1) * 4 * sizeof(unsigned int);
@@ -817,11 +862,27 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
             CK(cudaMemsetAsync(cs.b_trace.p, 0, bytes, cs.stream));
             park.trace = (unsigned int*)cs.b_trace.p;
         }
-        g_classes(k).episode(class_gs(h, k), cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop,
+        if (cs.grid2 > 0) { CK(cudaEventRecord(cs.done2, cs.stream)); CK(cudaStreamWaitEvent(cs.stream2, cs.done2, 0)); }   // queue / park counters are reset
+        cs.park = park;
+        g_classes(k).episode(h->image, class_gs(h, k), cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop,
                              h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                             park, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive);
+                             park, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive, cs.grid2 > 0 ? 0 : 1);
         CK(cudaMemcpyAsync(cs.h_n_alive, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, cs.stream));
         CK(cudaEventRecord(cs.t_end, cs.stream));
+        h->launches++;
+    }
+    // second launches (after ALL first launches, so that their CTAs queue behind them): the creatures a class could not seat
+    // in its first round, in wide groups, on the columns behind the first launch's
+    for (int k = N_CLASSES - 1; k >= 0 && !warp_mode; --k) {
+        ClassState& cs = h->cls[k];
+        if (!cs.n_batches || cs.grid2 <= 0) continue;
+        const int per1 = 32 >> class_gs(h, k);
+        const size_t first_block = ((size_t)cs.episode_grid * per1 + 31) / 32;
+        ParkPolicy park = cs.park;
+        park.trace = nullptr;
+        g_classes(k).episode(h->image, cs.gs2, cs.grid2, cs.stream2, cs.d_state + first_block * g_classes(k).words * 32, cs.d_lane_creature, cs.n_members,
+                             cs.d_queue, h->dpop, h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status,
+                             h->d_counters, park, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive, 1);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -857,6 +918,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
                 finished_now[k] = false;
                 if (!running[k]) continue;
                 cudaError_t q = cudaStreamQuery(h->cls[k].stream);       // BEFORE reading the counter: no slot can be missed
+                if (q == cudaSuccess && h->cls[k].grid2 > 0) q = cudaStreamQuery(h->cls[k].stream2);
                 if (q == cudaSuccess) finished_now[k] = true;
                 else if (q != cudaErrorNotReady) { h->err = std::string("episode kernel: ") + cudaGetErrorString(q); return REM2D_E_CUDA; }
                 CK(cudaMemcpyAsync(&h->h_poll[k], h->cls[k].d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, h->poll_stream));
@@ -870,7 +932,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
                 if (cnt > launched[k]) ++waited[k]; else waited[k] = 0;
                 if (cnt > launched[k] && (finished_now[k] || cnt - launched[k] >= 4 || waited[k] >= 3)) {
                     waited[k] = 0;
-                    g_classes(k).tail(h->opt.tail_group_shift, idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
+                    g_classes(k).tail(h->image, h->opt.tail_group_shift, idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
                                       h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
                                       trace ? (unsigned int*)cs.b_ttrace.p : nullptr);
                     CK(cudaGetLastError());
@@ -970,6 +1032,15 @@ int rem2d_get_counters(rem2d_handle* h, uint64_t* out) {
     cudaSetDevice(h->cfg.device);
     CK(cudaStreamSynchronize(h->user_stream));
     CK(cudaMemcpy(out, h->d_counters, sizeof(unsigned long long) * REM2D_N_COUNTERS, cudaMemcpyDeviceToHost));
+    return REM2D_OK;
+}
+// Diagnostics (libraries built with -DREM2D_PHASE_TIMING): warp-cycles per tick phase of the last evaluation,
+// out[(mode * 6 + gs) * 16 + phase], mode 0 = queue launches, 1 = tail launches; zeros in production builds.
+int rem2d_debug_phases(rem2d_handle* h, uint64_t* out) {
+    if (!h || !out) return REM2D_E_INVALID;
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->user_stream));
+    CK(cudaMemcpy(out, h->d_counters + REM2D_N_COUNTERS, sizeof(unsigned long long) * 12 * 16, cudaMemcpyDeviceToHost));
     return REM2D_OK;
 }
 

@@ -251,8 +251,22 @@ __host__ __device__ inline HotLayout make_hot_layout(const Layout& L, int gs) {
 // every member function TOGETHER; functions marked "leader" are executed by sub == 0 only and everything the other lanes need
 // afterwards is broadcast or read after a group barrier. With G == 1 the code degenerates to the sequential per-lane form.
 // Group barriers use the group's own lane mask, so groups of a warp never wait for each other inside a phase.
+// Phase timing (diagnostic builds only, -DREM2D_PHASE_TIMING: tools/phase_breakdown.py): clock64 deltas per tick phase
+#ifdef REM2D_PHASE_TIMING
+#define REM2D_N_PHASES 16
+#define PHASE(i) do { long long t_ = clock64(); ph[phase_cur] += t_ - phase_t0; phase_t0 = t_; phase_cur = (i); } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#endif
+enum { PH_LOOP, PH_CONTROL, PH_COLLIDE, PH_STAGE, PH_SCHEDULE, PH_VELOCITY, PH_STORE, PH_POSITION, PH_FINALIZE, PH_FINDNEW, PH_TOI_SCAN,
+       PH_TOI_EVENTS, PH_BUILD, PH_PARK };
+
 struct Sim {
     Layout L;
+#ifdef REM2D_PHASE_TIMING
+public:
+    long long ph[REM2D_N_PHASES]; long long phase_t0; int phase_cur;
+#endif
     int gs, G, sub, lead;     // lanes per creature = 1 << gs; my index in the group; absolute lane of the group leader
     unsigned gmask;           // lanes of my group
     int hj_off, hc_off, aux_off, sch_off;   // section rows of the hot block for this gs
@@ -304,6 +318,14 @@ struct Sim {
         return v;
     }
     __device__ __forceinline__ bool group_any(bool v) { return gs ? (__ballot_sync(gmask, v) != 0u) : v; }
+    // "does any lane that is executing this instruction together with me ..." - a scheduling hint only (results never depend on it)
+    __device__ __forceinline__ bool warp_any_converged(bool v) {
+#ifdef REM2D_EMU
+        return group_any(v);
+#else
+        return __any_sync(__activemask(), v) != 0;
+#endif
+    }
     __device__ __forceinline__ bool group_all(bool v) { return gs ? (__ballot_sync(gmask, v) == gmask) : v; }
     __device__ __forceinline__ float* hot_elem(int section, int count, int e) {     // field 0 of element e
         return h + ((section + (e >> e_shift) * count) << 5) + (e & e_mask);
@@ -401,6 +423,7 @@ struct Sim {
     // episode scalars of creature c (c < 0: empty column). Mirrors oracle world_build()/body_init(). Group-cooperative: bodies,
     // joints and the edge table are strided over the lanes of the group; ends with a group barrier.
     __device__ void build_world(const DevPop& p, int c) {
+        PHASE(PH_BUILD);
         if (c < 0) {
             if (leader()) { for (int w = 0; w < S_COUNT; ++w) g[w * 32] = 0.0f; setSi(S_NB, 0); setSi(S_ALIVE, 0); }
             nb = 0; nj = 0;
@@ -921,6 +944,78 @@ struct Sim {
         HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
     }
 
+    // The same solve arranged for the fused slots of the scheduled sweeps (solve_velocity): the friction of point 0 and the normal
+    // solve of a one-point manifold are straight-line code with predicated stores, so that the compiler can interleave them with
+    // the revolute solve another lane of the warp needs in the same slot; the two-point manifold continues in a branch. Every
+    // path performs exactly the operations of contact_solve_velocity.
+    __device__ __forceinline__ void contact_solve_velocity_fused(float* hc, const int st, const bool pred, const int meta) {
+        const int b = meta & 0xff, count = (meta >> 8) & 3;
+        const float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
+        V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
+        const V2 normal = mk(hc[HC_NX * st], hc[HC_NY * st]), tangent = cross_vs(normal, 1.0f);
+        const float friction = k->friction;
+        const V2 r0 = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
+        const float ni0 = hc[HC_NI0 * st];
+        {   // friction, point 0
+            V2 dv = vB + cross_sv(wB, r0);
+            float vt = dot(dv, tangent);
+            float lambda = hc[HC_TM0 * st] * (-vt);
+            float ti = hc[HC_TI0 * st];
+            float maxF = friction * ni0;
+            float ni = clampf(ti + lambda, -maxF, maxF);
+            lambda = ni - ti;
+            if (pred) hc[HC_TI0 * st] = ni;
+            V2 P = lambda * tangent;
+            vB = vB + mB * P; wB += iB * cross(r0, P);
+        }
+        {   // one-point manifold: normal constraint
+            V2 dv = vB + cross_sv(wB, r0);
+            float vn = dot(dv, normal);
+            float lambda = -hc[HC_NM0 * st] * vn;
+            float ni = max2(ni0 + lambda, 0.0f);
+            lambda = ni - ni0;
+            V2 P = lambda * normal;
+            const V2 v1 = vB + mB * P; const float w1 = wB + iB * cross(r0, P);
+            if (pred && count == 1) {
+                hc[HC_NI0 * st] = ni;
+                HB(HB_VX, b) = v1.x; HB(HB_VY, b) = v1.y; HB(HB_W, b) = w1;
+            }
+        }
+        if (pred && count != 1) {
+            V2 r1 = mk(hc[HC_R1X * st], hc[HC_R1Y * st]);
+            {   // friction, point 1
+                V2 dv = vB + cross_sv(wB, r1);
+                float vt = dot(dv, tangent);
+                float lambda = hc[HC_TM1 * st] * (-vt);
+                float ti = hc[HC_TI1 * st];
+                float maxF = friction * hc[HC_NI1 * st];
+                float ni = clampf(ti + lambda, -maxF, maxF);
+                lambda = ni - ti; hc[HC_TI1 * st] = ni;
+                V2 P = lambda * tangent;
+                vB = vB + mB * P; wB += iB * cross(r1, P);
+            }
+            float a1 = ni0, a2 = hc[HC_NI1 * st];
+            V2 dv1 = vB + cross_sv(wB, r0), dv2 = vB + cross_sv(wB, r1);
+            float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+            float k11 = hc[HC_K11 * st], k12 = hc[HC_K12 * st], k22 = hc[HC_K22 * st];
+            float bx = vn1 - (k11 * a1 + k12 * a2), by = vn2 - (k12 * a1 + k22 * a2);
+            float x1, x2; bool solved = false;
+            x1 = -(hc[HC_IXX * st] * bx + hc[HC_IXY * st] * by); x2 = -(hc[HC_IXY * st] * bx + hc[HC_IYY * st] * by);
+            if (x1 >= 0.0f && x2 >= 0.0f) solved = true;
+            if (!solved) { x1 = -hc[HC_NM0 * st] * bx; x2 = 0.0f; vn2 = k12 * x1 + by; if (x1 >= 0.0f && vn2 >= 0.0f) solved = true; }
+            if (!solved) { x1 = 0.0f; x2 = -hc[HC_NM1 * st] * by; vn1 = k12 * x2 + bx; if (x2 >= 0.0f && vn1 >= 0.0f) solved = true; }
+            if (!solved) { x1 = 0.0f; x2 = 0.0f; if (bx >= 0.0f && by >= 0.0f) solved = true; }
+            if (solved) {
+                float d1 = x1 - a1, d2 = x2 - a2;
+                V2 P1 = d1 * normal, P2 = d2 * normal;
+                vB = vB + mB * (P1 + P2);
+                wB += iB * (cross(r0, P1) + cross(r1, P2));
+                hc[HC_NI0 * st] = x1; hc[HC_NI1 * st] = x2;
+            }
+            HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+        }
+    }
+
     __device__ __forceinline__ void count_contact_solves(int nt, int vit) {
         int n1 = 0, n2 = 0;
         for_contacts(nt, [&](float* hc, const int st, int) { if (((__float_as_int(hc[HC_META * st]) >> 8) & 3) == 1) ++n1; else ++n2; });
@@ -997,8 +1092,10 @@ struct Sim {
     // Here both candidates are computed unconditionally from the same inputs and the results are selected: the two
     // dependency chains overlap, there is no reconvergence overhead, and every value is bit-identical to the branchy
     // evaluation (each candidate uses exactly the operations of its Box2D path).
-    __device__ __forceinline__ void joint_solve_velocity(int s) {
-        const int meta = HJi(HJ_META, s);
+    // `pred` = false: the lane only goes through the motions (fused slots, see solve_velocity): loads and arithmetic on a valid
+    // slot, no stores.
+    __device__ __forceinline__ void joint_solve_velocity(int s, const bool pred = true) { joint_solve_velocity(s, pred, HJi(HJ_META, s)); }
+    __device__ __forceinline__ void joint_solve_velocity(int s, const bool pred, const int meta) {
         const int a = meta & 0xff, b = (meta >> 8) & 0xff, limit = (meta >> 16) & 3;
         const float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
         V2 vA = mk(HB(HB_VX, a), HB(HB_VY, a)); float wA = HB(HB_W, a);
@@ -1013,7 +1110,7 @@ struct Sim {
             float oldImpulse = HJ(HJ_MIMP, s);
             float maxImpulse = HJ(HJ_MAXIMP, s);
             float ni = clampf(oldImpulse + impulse, -maxImpulse, maxImpulse);
-            HJ(HJ_MIMP, s) = ni;
+            if (pred) HJ(HJ_MIMP, s) = ni;
             impulse = ni - oldImpulse;
             wA -= iA * impulse; wB += iB * impulse;
         }
@@ -1045,11 +1142,13 @@ struct Sim {
         const float jz3 = reduce ? 0.0f : jz + iz;
         // ---- select
         const bool act = limit != 0;
-        HJ(HJ_IMPX, s) = jx + (act ? px : imp2.x);
-        HJ(HJ_IMPY, s) = jy + (act ? py : imp2.y);
-        if (act) HJ(HJ_IMPZ, s) = jz3;
-        HB(HB_VX, a) = act ? vA3.x : vA2.x; HB(HB_VY, a) = act ? vA3.y : vA2.y; HB(HB_W, a) = act ? wA3 : wA2;
-        HB(HB_VX, b) = act ? vB3.x : vB2.x; HB(HB_VY, b) = act ? vB3.y : vB2.y; HB(HB_W, b) = act ? wB3 : wB2;
+        if (pred) {
+            HJ(HJ_IMPX, s) = jx + (act ? px : imp2.x);
+            HJ(HJ_IMPY, s) = jy + (act ? py : imp2.y);
+            if (act) HJ(HJ_IMPZ, s) = jz3;
+            HB(HB_VX, a) = act ? vA3.x : vA2.x; HB(HB_VY, a) = act ? vA3.y : vA2.y; HB(HB_W, a) = act ? wA3 : wA2;
+            HB(HB_VX, b) = act ? vB3.x : vB2.x; HB(HB_VY, b) = act ? vB3.y : vB2.y; HB(HB_W, b) = act ? wB3 : wB2;
+        }
     }
     __device__ __forceinline__ bool joint_solve_position(int s) {
         int meta = HJi(PJ_META, s);
@@ -1228,6 +1327,7 @@ struct Sim {
             }
         }
         nt_out = nt;
+        PHASE(PH_SCHEDULE);
         build_schedule(nt, false);
         return true;
     }
@@ -1366,18 +1466,35 @@ struct Sim {
     // ---------------- velocity iterations: the hot loop (everything in shared memory)
     // NB: equal limits (|upper-lower| < 2*angularSlop) do not occur: limits are -+pi/2 (module_utility.py:28-29)
     __device__ void solve_velocity(int nt) {
+        PHASE(PH_VELOCITY);
         const int vit = k->vel_iters;
         if (sched_P) {
             const int P = sched_P, total = (vit + sched_smax) * P;
             int pslot = 0, T = 0;
+            // the schedule and the constraints' index words are constant during the sweeps: the next slot's entry and index
+            // word are fetched while the current slot computes (they head the slot's chain of dependent shared-memory loads)
+            int e = SCH(0, sub);
+            int meta = __float_as_int(hot_elem((e & SCH_CONTACT) ? hc_off : hj_off, (e & SCH_CONTACT) ? HC_COUNT : HJ_COUNT, e < 0 ? (e & 0xff) : 0)[0]);
             for (int q = 0; q < total; ++q) {
-                const int e = SCH(pslot, sub);
+                int pnext = pslot + 1, Tnext = T;
+                if (pnext == P) { pnext = 0; ++Tnext; }
+                const int e_next = SCH(pnext, sub);
+                const int meta_next = __float_as_int(hot_elem((e_next & SCH_CONTACT) ? hc_off : hj_off, (e_next & SCH_CONTACT) ? HC_COUNT : HJ_COUNT,
+                                                              e_next < 0 ? (e_next & 0xff) : 0)[0]);
                 const int it = T - ((e >> 8) & 0xff);
                 const bool act = e < 0 && it >= 0 && it < vit;
-                if (act && !(e & SCH_CONTACT)) joint_solve_velocity(e & 0xff);
-                if (act && (e & SCH_CONTACT)) contact_solve_velocity(hot_elem(hc_off, HC_COUNT, e & 0xff), 32);
+                const bool isj = act && !(e & SCH_CONTACT), isc = act && (e & SCH_CONTACT);
+                // A slot in which some lane of the warp has a contact: EVERY lane runs the revolute solve and the contact solve
+                // back to back as straight-line code with predicated stores (idle lanes go through the motions on slot 0), so
+                // the two dependency chains overlap instead of being serialised by a divergent branch - the slot takes about
+                // max(joint, contact) instead of their sum, which is what bounds the tick latency of a wide group.
+                if (warp_any_converged(isc)) {
+                    // (index word 0 for the idle lanes: bodies 0 / 0, always valid addresses)
+                    joint_solve_velocity(isj ? (e & 0xff) : 0, isj, isj ? meta : 0);
+                    contact_solve_velocity_fused(hot_elem(hc_off, HC_COUNT, isc ? (e & 0xff) : 0), 32, isc, isc ? meta : 0);
+                } else if (isj) joint_solve_velocity(e & 0xff, true, meta);
                 gsync();
-                if (++pslot == P) { pslot = 0; ++T; }
+                pslot = pnext; T = Tnext; e = e_next; meta = meta_next;
             }
             return;
         }
@@ -1389,6 +1506,7 @@ struct Sim {
         gsync();
     }
     __device__ void solve_post(int nt) {
+        PHASE(PH_STORE);
         const float hdt = k->dt;
         const int vit = k->vel_iters;
         if (leader()) cnt.c[REM2D_CNT_JOINT_VSOLVES] += (unsigned)(vit * nj);
@@ -1429,6 +1547,7 @@ struct Sim {
             HB(HB_VX, b) = c.x; HB(HB_VY, b) = c.y; HB(HB_W, b) = a;
         }
         gsync();
+        PHASE(PH_POSITION);
         int positionSolved = 0;
         const int pit = k->pos_iters;
         const int psmax = sched_smax + (nt > 0 ? 1 : 0);
@@ -1495,6 +1614,7 @@ struct Sim {
         }
         gsync();
         // copy back, synchronize transforms, sleep management
+        PHASE(PH_FINALIZE);
         float minSleepTime = RB_MAXF;
         for (int b = sub; b < nb; b += G) {
             B(BF_CX, b) = HB(HB_VX, b); B(BF_CY, b) = HB(HB_VY, b); B(BF_A, b) = HB(HB_W, b);
@@ -1514,6 +1634,7 @@ struct Sim {
             for (int b = sub; b < nb; b += G) set_awake(b, false);
         for (int b = sub; b < nb; b += G) synchronize_fixtures(b);      // (independent per body: any order)
         gsync();
+        PHASE(PH_FINDNEW);
         find_new_contacts_group();
     }
 
@@ -1777,6 +1898,7 @@ struct Sim {
     // in the pool (toi + toiFlag) exactly as Box2D caches them; the leader then runs Box2D's loop, which finds the cached
     // values, and handles TOI events (rare: 2 % of the ticks) sequentially.
     __device__ void solve_toi() {
+        PHASE(PH_TOI_SCAN);
         const float dt = k->dt;
         for (int b = sub; b < nb; b += G) { setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) & ~BFL_ISLAND); B(BF_ALPHA0, b) = 0.0f; }
         if (leader()) {   // alpha0 of the static edge bodies: clear what the previous step dirtied
@@ -1800,6 +1922,7 @@ struct Sim {
             C(CF_TOI, c) = alpha;
         }
         gsync();
+        PHASE(PH_TOI_EVENTS);
         if (leader()) solve_toi_events(dt);
         gsync();
     }
@@ -1910,6 +2033,7 @@ struct Sim {
     // ---- Modular2D.step + the body of evaluate()'s loop: tick_pre -> solve_velocity -> tick_post, all group-cooperative.
     // b2World::Step = FindNewContacts (first step) -> Collide -> Solve -> SolveTOI.
     __device__ bool tick_pre(int& nt) {
+        PHASE(PH_CONTROL);
         if (leader()) {
             double wod = Sd(S_WOD_LO) + k->wod_speed;
             setSd(S_WOD_LO, wod);
@@ -1930,19 +2054,23 @@ struct Sim {
         const int newfix = bcast(Si(S_NEWFIX));
         gsync();
         if (newfix) {
+            PHASE(PH_FINDNEW);
             find_new_contacts_group();
             if (leader()) setSi(S_NEWFIX, 0);
             gsync();
         }
         float dtRatio = S(S_INVDT0) * dt;
+        PHASE(PH_COLLIDE);
         collide();
         nt = 0;
+        PHASE(PH_STAGE);
         return dt > 0.0f ? solve_pre(dtRatio, nt) : false;
     }
     __device__ void tick_post(bool solved, int nt) {
         const float dt = k->dt;
         if (solved) solve_post(nt);
         if (k->continuous && dt > 0.0f) solve_toi();
+        PHASE(PH_LOOP);
         if (leader()) {
             if (dt > 0.0f) S(S_INVDT0) = 1.0f / dt;
             cnt.c[REM2D_CNT_TICKS]++;
