@@ -102,6 +102,53 @@ def cpu_baseline(pop, ys, sample_creatures, threads):
     return float(ticks.sum()) / dt, dt, sub.n_creatures, int(ticks.sum()), fit, ticks
 
 
+def ea_bench(args, rank, local_rank, world, cores):
+    """BASELINE config 5: the EA generation loop at population --pop. Rank 0 runs selection / variation / expansion (persistent
+    worker pool) and drives the evaluation; with N > 1 ranks the generation's table is broadcast and every rank evaluates its
+    shard (distributed.evaluate_broadcast). Prints per-generation expand / evaluate seconds and creature-steps/s."""
+    import random
+    from gym_rem2d_b200 import ea
+    cfg = ea.default_config(enc=args.encoding.split(",")[0], mr=0.01, mmr=0.01, ms=0.1)      # 0.cfg-like rates
+    cfg["ea"]["batch_size"] = str(args.pop)
+    run = None
+    if rank == 0:
+        random.seed(args.seed)
+        np.random.seed(args.seed)
+        run = ea.run2D(cfg, "", workers=max(2, cores - 2), distributed=world > 1)     # pool first: before CUDA exists here
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    if rank != 0:
+        from gym_rem2d_b200 import distributed as rdist
+        from gym_rem2d_b200.env import BatchedModular2D
+        env = BatchedModular2D(device=local_rank)
+        env.seed(K.TERRAIN_SEED)
+        rdist.serve_evaluations(env.engine, K.EVALUATION_STEPS)
+        dist.destroy_process_group()
+        return
+    t0 = time.perf_counter()
+    run.run_deap(cfg, n_generations=args.generations)
+    total = time.perf_counter() - t0
+    if world > 1:
+        from gym_rem2d_b200 import distributed as rdist
+        rdist.broadcast_table(None, 0)              # stop signal for the serving ranks
+    gens = run.generation_log
+    steps = sum(g["creature_steps"] for g in gens)
+    secs = sum(g["seconds"] for g in gens)
+    print(json.dumps({"metric": "creature-steps/sec (EA loop, config 5)", "value": steps * (world if world > 1 else 1) / secs if world == 1 else None,
+                      "unit": "creature-steps/s", "n_gpus": world, "population": args.pop, "generations": len(gens), "host_workers": max(2, cores - 2),
+                      "seconds_per_generation": secs / max(1, len(gens)),
+                      "per_generation": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in g.items()} for g in gens],
+                      "note": "expand_s = selection + clone + mutate + genome.create + flatten in the worker pool (host Python); evaluate_s = "
+                              "GPU evaluation; with pipelining evaluate_s is hidden inside the expansion (evaluate_hidden_s)",
+                      "initial_population_s": round(total - secs, 2)}))
+    run.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -112,6 +159,8 @@ def main():
     ap.add_argument("--encoding", default="lsystem")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ea", action="store_true", help="config 5: generations of the batched EA loop (REM2D_main.py:280-348) at --pop")
+    ap.add_argument("--generations", type=int, default=2)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -148,6 +197,10 @@ def main():
                                        "is not installable, this is the float32 C restatement oracle/rem2d_oracle.c" % sample},
             "e2e": {"value": value, "unit": "creature-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+
+    # ------------------------------------------------------------------ config 5: the EA generation loop
+    if args.ea:
+        return ea_bench(args, rank, local_rank, world, cores)
 
     # ------------------------------------------------------------------ our arm
     # host-side expansion first (process pool; must happen before CUDA is initialised in this process)

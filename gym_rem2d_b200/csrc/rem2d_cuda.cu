@@ -167,7 +167,7 @@ struct Options {
     int min_class = 0;
     int group_shift = -1;        // log2 lanes per creature in the queue / step kernels (-1: per class default)
     int class_gs[N_CLASSES] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per capacity class ("class_gs_<k>", -1: default)
-    int tail_group_shift = 3;    // log2 lanes per creature of the tail launches (measured: 8 lanes tick a large creature as fast as 32)
+    int tail_group_shift = 5;    // log2 lanes per creature of the tail launches (few creatures are parked by default: a warp each)
     int second_group_shift = -1; // log2 lanes per creature of a second launch for the creatures a large class cannot seat in its first
                                  // round (-1: off = refill the first launch's lanes). Measured and rejected as default: the GPU is
                                  // still throughput-bound when the first round ends, wide groups only add issue load (+25 % run time)
@@ -436,7 +436,7 @@ static int launch_reset(rem2d_handle* h);
 // proportion to their work; a class never gets more warps than it has creatures, and what it cannot use is handed to the
 // others. Without this the largest class would occupy every SM until its last creature dies and the remaining classes would
 // run after it. Returns true iff EVERY creature of every class has a group from the start (one round, under-filled GPU).
-static bool size_grids(rem2d_handle* h) {
+static bool size_grids(rem2d_handle* h, double warp_frac = 0.97) {
     const double smem_kb = h->opt.smem_budget_kb, small_weight = h->opt.small_weight;
     double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98;
     double work[N_CLASSES], smem[N_CLASSES];
@@ -456,7 +456,7 @@ static bool size_grids(rem2d_handle* h) {
     // The register file bounds the resident warps as well (h->max_warps_per_sm, from the occupancy API): a launch whose
     // CTAs do not fit waits for the CTAs of the classes launched before it to EXIT, which serialises the classes
     // (measured: the small classes started 400 ms late when 9 warps per SM fit and the grids asked for 9.7).
-    double warp_budget = (double)h->n_sms * h->max_warps_per_sm[h->image] * 0.97;
+    double warp_budget = (double)h->n_sms * h->max_warps_per_sm[h->image] * warp_frac;
     bool all_fit = true;
     for (int round = 0; round <= N_CLASSES; ++round) {
         double denom = 0.0, wsum = 0.0;
@@ -506,11 +506,12 @@ static void choose_groups_and_grids(rem2d_handle* h) {
     if (!all_fit) { h->image = 0; size_grids(h); }
     for (int k = 0; k < N_CLASSES; ++k) { h->cls[k].grid2 = 0; h->cls[k].gs2 = 0; }
     if (!all_fit) {
-        // Throughput-bound population: one lane per creature in the first round. The creatures of the LARGE classes that do
-        // not get a lane then are not run by refilled lanes - one more lap at the bulk tick latency (2.2 ms for 17-21 bodies)
-        // that would start when the first lap ends and push the long-lived creatures among them to the end of the run - but
-        // by a second launch with wide groups (2-4x lower tick latency) whose CTAs become resident as the first launch's
-        // warps exit: by then the small classes are draining and issue slots are free.
+        // Throughput-bound population: one lane per creature, lanes refilled from the class queue. OPTION "second_group_shift"
+        // (off by default): the creatures of the large classes that do not get a lane in the first round are run by a second
+        // launch with wide groups (2-4x lower tick latency) whose CTAs become resident as the first launch's warps exit,
+        // instead of one more lap at the bulk tick latency. Measured on the bench population: the GPU is still
+        // throughput-bound when the first round ends (the small classes run until ~550 ms), so the wide groups only add issue
+        // load: 1050-1200 ms against 815-880 ms with refill.
         const int gs2 = h->opt.second_group_shift;
         for (int k = 0; k < N_CLASSES && gs2 >= 0; ++k) {
             ClassState& cs = h->cls[k];
@@ -522,15 +523,16 @@ static void choose_groups_and_grids(rem2d_handle* h) {
         }
         return;
     }
-    for (bool progress = true; progress;) {
-        progress = false;
-        for (int k = N_CLASSES - 1; k >= 0; --k) {
-            if (forced[k] || !h->cls[k].n_members || h->cur_gs[k] >= g_classes(k).gs) continue;
-            h->cur_gs[k] += 1;
-            if (size_grids(h)) progress = true;
-            else h->cur_gs[k] -= 1;
-        }
+    // widest uniform group width (capped per class) with which every creature has a group from the start AND the warps fill
+    // at most 60 % of the resident-warp limit: wide groups are issue-bound before the SMs are full. Measured optimum
+    // (tools/small_pop.py): 16384 creatures -> 4 lanes, 8192 -> 8, 4096 -> 8-16, <= 1024 -> 32
+    for (int gs = 5; gs >= 1; --gs) {
+        for (int k = 0; k < N_CLASSES; ++k)
+            if (!forced[k]) h->cur_gs[k] = std::min(gs, g_classes(k).gs);
+        if (size_grids(h, 0.6)) { size_grids(h); return; }
     }
+    for (int k = 0; k < N_CLASSES; ++k)
+        if (!forced[k]) h->cur_gs[k] = 0;
     size_grids(h);
 }
 
@@ -802,8 +804,8 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     // ones leave the longest-lived creatures on the slow path. Drain / late-start parking never paid off. The number of
     // parked creatures per class is bounded (n/16, at most 4 per SM): in an evolved population where most creatures live
     // long, the rest simply stay on their lanes.
-    int park_ticks = 256;
-    double cap_frac = 1.0 / 16.0;
+    int park_ticks = 200;            // measured (tools/sweep_groups.py, 65536 creatures): 256 -> 820 ms, 200 -> 790 ms, 160 -> 930 ms
+    double cap_frac = 0.25;
     {   // Under-filled GPU (every creature of every class has a group from the start, e.g. 16384 creatures): tail warps find
         // free SM resources, so parking earlier pays (16384 creatures: 450 -> 413 ms with 160 ticks and a quarter of a class).
         bool single_round = true;

@@ -944,76 +944,87 @@ public:
         HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
     }
 
-    // The same solve arranged for the fused slots of the scheduled sweeps (solve_velocity): the friction of point 0 and the normal
-    // solve of a one-point manifold are straight-line code with predicated stores, so that the compiler can interleave them with
-    // the revolute solve another lane of the warp needs in the same slot; the two-point manifold continues in a branch. Every
-    // path performs exactly the operations of contact_solve_velocity.
-    __device__ __forceinline__ void contact_solve_velocity_fused(float* hc, const int st, const bool pred, const int meta) {
-        const int b = meta & 0xff, count = (meta >> 8) & 3;
-        const float mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
-        V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
-        const V2 normal = mk(hc[HC_NX * st], hc[HC_NY * st]), tangent = cross_vs(normal, 1.0f);
+    // The same solve in three pieces - loads, arithmetic, stores - for the FUSED slots of the scheduled sweeps (solve_velocity):
+    // a slot in which lanes of the warp hold a revolute joint and other lanes a contact runs both kinds as ONE straight-line
+    // sequence (all loads, both computations, then the stores), so the two dependency chains overlap instead of being
+    // serialised by a divergent branch. Friction of point 0 and the normal solve of a one-point manifold are straight-line;
+    // a two-point manifold continues from the post-friction velocity in contact_v_two. Every path performs exactly the
+    // operations of contact_solve_velocity.
+    struct CV { int b, count; float mB, iB, wB, tm0, ti0, ni0, nm0, o_ti0, o_ni0, wF, w1; V2 vB, normal, tangent, r0, vF, v1; };
+    __device__ __forceinline__ void contact_v_load(const float* hc, const int st, const int meta, CV& c) {
+        c.b = meta & 0xff; c.count = (meta >> 8) & 3;
+        c.mB = HB(HB_INVM, c.b); c.iB = HB(HB_INVI, c.b);
+        c.vB = mk(HB(HB_VX, c.b), HB(HB_VY, c.b)); c.wB = HB(HB_W, c.b);
+        c.normal = mk(hc[HC_NX * st], hc[HC_NY * st]); c.tangent = cross_vs(c.normal, 1.0f);
+        c.r0 = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
+        c.tm0 = hc[HC_TM0 * st]; c.ti0 = hc[HC_TI0 * st]; c.ni0 = hc[HC_NI0 * st]; c.nm0 = hc[HC_NM0 * st];
+    }
+    __device__ __forceinline__ void contact_v_compute(CV& c) {
         const float friction = k->friction;
-        const V2 r0 = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
-        const float ni0 = hc[HC_NI0 * st];
+        V2 vB = c.vB; float wB = c.wB;
         {   // friction, point 0
-            V2 dv = vB + cross_sv(wB, r0);
-            float vt = dot(dv, tangent);
-            float lambda = hc[HC_TM0 * st] * (-vt);
-            float ti = hc[HC_TI0 * st];
-            float maxF = friction * ni0;
-            float ni = clampf(ti + lambda, -maxF, maxF);
-            lambda = ni - ti;
-            if (pred) hc[HC_TI0 * st] = ni;
-            V2 P = lambda * tangent;
-            vB = vB + mB * P; wB += iB * cross(r0, P);
+            V2 dv = vB + cross_sv(wB, c.r0);
+            float vt = dot(dv, c.tangent);
+            float lambda = c.tm0 * (-vt);
+            float maxF = friction * c.ni0;
+            float ni = clampf(c.ti0 + lambda, -maxF, maxF);
+            lambda = ni - c.ti0; c.o_ti0 = ni;
+            V2 P = lambda * c.tangent;
+            vB = vB + c.mB * P; wB += c.iB * cross(c.r0, P);
         }
+        c.vF = vB; c.wF = wB;
         {   // one-point manifold: normal constraint
-            V2 dv = vB + cross_sv(wB, r0);
-            float vn = dot(dv, normal);
-            float lambda = -hc[HC_NM0 * st] * vn;
-            float ni = max2(ni0 + lambda, 0.0f);
-            lambda = ni - ni0;
-            V2 P = lambda * normal;
-            const V2 v1 = vB + mB * P; const float w1 = wB + iB * cross(r0, P);
-            if (pred && count == 1) {
-                hc[HC_NI0 * st] = ni;
-                HB(HB_VX, b) = v1.x; HB(HB_VY, b) = v1.y; HB(HB_W, b) = w1;
-            }
+            V2 dv = vB + cross_sv(wB, c.r0);
+            float vn = dot(dv, c.normal);
+            float lambda = -c.nm0 * vn;
+            float ni = max2(c.ni0 + lambda, 0.0f);
+            lambda = ni - c.ni0; c.o_ni0 = ni;
+            V2 P = lambda * c.normal;
+            c.v1 = vB + c.mB * P; c.w1 = wB + c.iB * cross(c.r0, P);
         }
-        if (pred && count != 1) {
-            V2 r1 = mk(hc[HC_R1X * st], hc[HC_R1Y * st]);
-            {   // friction, point 1
-                V2 dv = vB + cross_sv(wB, r1);
-                float vt = dot(dv, tangent);
-                float lambda = hc[HC_TM1 * st] * (-vt);
-                float ti = hc[HC_TI1 * st];
-                float maxF = friction * hc[HC_NI1 * st];
-                float ni = clampf(ti + lambda, -maxF, maxF);
-                lambda = ni - ti; hc[HC_TI1 * st] = ni;
-                V2 P = lambda * tangent;
-                vB = vB + mB * P; wB += iB * cross(r1, P);
-            }
-            float a1 = ni0, a2 = hc[HC_NI1 * st];
-            V2 dv1 = vB + cross_sv(wB, r0), dv2 = vB + cross_sv(wB, r1);
-            float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-            float k11 = hc[HC_K11 * st], k12 = hc[HC_K12 * st], k22 = hc[HC_K22 * st];
-            float bx = vn1 - (k11 * a1 + k12 * a2), by = vn2 - (k12 * a1 + k22 * a2);
-            float x1, x2; bool solved = false;
-            x1 = -(hc[HC_IXX * st] * bx + hc[HC_IXY * st] * by); x2 = -(hc[HC_IXY * st] * bx + hc[HC_IYY * st] * by);
-            if (x1 >= 0.0f && x2 >= 0.0f) solved = true;
-            if (!solved) { x1 = -hc[HC_NM0 * st] * bx; x2 = 0.0f; vn2 = k12 * x1 + by; if (x1 >= 0.0f && vn2 >= 0.0f) solved = true; }
-            if (!solved) { x1 = 0.0f; x2 = -hc[HC_NM1 * st] * by; vn1 = k12 * x2 + bx; if (x2 >= 0.0f && vn1 >= 0.0f) solved = true; }
-            if (!solved) { x1 = 0.0f; x2 = 0.0f; if (bx >= 0.0f && by >= 0.0f) solved = true; }
-            if (solved) {
-                float d1 = x1 - a1, d2 = x2 - a2;
-                V2 P1 = d1 * normal, P2 = d2 * normal;
-                vB = vB + mB * (P1 + P2);
-                wB += iB * (cross(r0, P1) + cross(r1, P2));
-                hc[HC_NI0 * st] = x1; hc[HC_NI1 * st] = x2;
-            }
-            HB(HB_VX, b) = vB.x; HB(HB_VY, b) = vB.y; HB(HB_W, b) = wB;
+    }
+    __device__ __forceinline__ void contact_v_store1(float* hc, const int st, const CV& c) {
+        hc[HC_TI0 * st] = c.o_ti0;
+        if (c.count == 1) {
+            hc[HC_NI0 * st] = c.o_ni0;
+            HB(HB_VX, c.b) = c.v1.x; HB(HB_VY, c.b) = c.v1.y; HB(HB_W, c.b) = c.w1;
         }
+    }
+    __device__ __forceinline__ void contact_v_two(float* hc, const int st, const CV& c) {
+        V2 vB = c.vF; float wB = c.wF;
+        const V2 normal = c.normal, tangent = c.tangent, r0 = c.r0;
+        const float mB = c.mB, iB = c.iB, friction = k->friction;
+        V2 r1 = mk(hc[HC_R1X * st], hc[HC_R1Y * st]);
+        {   // friction, point 1
+            V2 dv = vB + cross_sv(wB, r1);
+            float vt = dot(dv, tangent);
+            float lambda = hc[HC_TM1 * st] * (-vt);
+            float ti = hc[HC_TI1 * st];
+            float maxF = friction * hc[HC_NI1 * st];
+            float ni = clampf(ti + lambda, -maxF, maxF);
+            lambda = ni - ti; hc[HC_TI1 * st] = ni;
+            V2 P = lambda * tangent;
+            vB = vB + mB * P; wB += iB * cross(r1, P);
+        }
+        float a1 = c.ni0, a2 = hc[HC_NI1 * st];
+        V2 dv1 = vB + cross_sv(wB, r0), dv2 = vB + cross_sv(wB, r1);
+        float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+        float k11 = hc[HC_K11 * st], k12 = hc[HC_K12 * st], k22 = hc[HC_K22 * st];
+        float bx = vn1 - (k11 * a1 + k12 * a2), by = vn2 - (k12 * a1 + k22 * a2);
+        float x1, x2; bool solved = false;
+        x1 = -(hc[HC_IXX * st] * bx + hc[HC_IXY * st] * by); x2 = -(hc[HC_IXY * st] * bx + hc[HC_IYY * st] * by);
+        if (x1 >= 0.0f && x2 >= 0.0f) solved = true;
+        if (!solved) { x1 = -c.nm0 * bx; x2 = 0.0f; vn2 = k12 * x1 + by; if (x1 >= 0.0f && vn2 >= 0.0f) solved = true; }
+        if (!solved) { x1 = 0.0f; x2 = -hc[HC_NM1 * st] * by; vn1 = k12 * x2 + bx; if (x2 >= 0.0f && vn1 >= 0.0f) solved = true; }
+        if (!solved) { x1 = 0.0f; x2 = 0.0f; if (bx >= 0.0f && by >= 0.0f) solved = true; }
+        if (solved) {
+            float d1 = x1 - a1, d2 = x2 - a2;
+            V2 P1 = d1 * normal, P2 = d2 * normal;
+            vB = vB + mB * (P1 + P2);
+            wB += iB * (cross(r0, P1) + cross(r1, P2));
+            hc[HC_NI0 * st] = x1; hc[HC_NI1 * st] = x2;
+        }
+        HB(HB_VX, c.b) = vB.x; HB(HB_VY, c.b) = vB.y; HB(HB_W, c.b) = wB;
     }
 
     __device__ __forceinline__ void count_contact_solves(int nt, int vit) {
@@ -1092,25 +1103,33 @@ public:
     // Here both candidates are computed unconditionally from the same inputs and the results are selected: the two
     // dependency chains overlap, there is no reconvergence overhead, and every value is bit-identical to the branchy
     // evaluation (each candidate uses exactly the operations of its Box2D path).
-    // `pred` = false: the lane only goes through the motions (fused slots, see solve_velocity): loads and arithmetic on a valid
-    // slot, no stores.
-    __device__ __forceinline__ void joint_solve_velocity(int s, const bool pred = true) { joint_solve_velocity(s, pred, HJi(HJ_META, s)); }
-    __device__ __forceinline__ void joint_solve_velocity(int s, const bool pred, const int meta) {
-        const int a = meta & 0xff, b = (meta >> 8) & 0xff, limit = (meta >> 16) & 3;
-        const float mA = HB(HB_INVM, a), iA = HB(HB_INVI, a), mB = HB(HB_INVM, b), iB = HB(HB_INVI, b);
-        V2 vA = mk(HB(HB_VX, a), HB(HB_VY, a)); float wA = HB(HB_W, a);
-        V2 vB = mk(HB(HB_VX, b), HB(HB_VY, b)); float wB = HB(HB_W, b);
-        const V2 rA = mk(HJ(HJ_RAX, s), HJ(HJ_RAY, s)), rB = mk(HJ(HJ_RBX, s), HJ(HJ_RBY, s));
-        const float exx = HJ(HJ_EXX, s), eyx = HJ(HJ_EYX, s), eyy = HJ(HJ_EYY, s);
-        const float d2 = HJ(HJ_INV2, s), det = HJ(HJ_INV3, s);
-        const float jx = HJ(HJ_IMPX, s), jy = HJ(HJ_IMPY, s), jz = HJ(HJ_IMPZ, s);
+    // Loads / arithmetic / stores of the solve as separate pieces (see CV above for why).
+    struct JV { int a, b, limit; bool act; float mA, iA, mB, iB, wA, wB, exx, eyx, eyy, d2, det, jx, jy, jz, mspeed, mmass, mimp, maximp;
+                float o_mimp, o_jx, o_jy, o_jz, o_wA, o_wB; V2 vA, vB, rA, rB, o_vA, o_vB; };
+    __device__ __forceinline__ void joint_v_load(int s, const int meta, JV& r) {
+        r.a = meta & 0xff; r.b = (meta >> 8) & 0xff; r.limit = (meta >> 16) & 3;
+        r.mA = HB(HB_INVM, r.a); r.iA = HB(HB_INVI, r.a); r.mB = HB(HB_INVM, r.b); r.iB = HB(HB_INVI, r.b);
+        r.vA = mk(HB(HB_VX, r.a), HB(HB_VY, r.a)); r.wA = HB(HB_W, r.a);
+        r.vB = mk(HB(HB_VX, r.b), HB(HB_VY, r.b)); r.wB = HB(HB_W, r.b);
+        r.rA = mk(HJ(HJ_RAX, s), HJ(HJ_RAY, s)); r.rB = mk(HJ(HJ_RBX, s), HJ(HJ_RBY, s));
+        r.exx = HJ(HJ_EXX, s); r.eyx = HJ(HJ_EYX, s); r.eyy = HJ(HJ_EYY, s);
+        r.d2 = HJ(HJ_INV2, s); r.det = HJ(HJ_INV3, s);
+        r.jx = HJ(HJ_IMPX, s); r.jy = HJ(HJ_IMPY, s); r.jz = HJ(HJ_IMPZ, s);
+        r.mspeed = HJ(HJ_MSPEED, s); r.mmass = HJ(HJ_MMASS, s); r.mimp = HJ(HJ_MIMP, s); r.maximp = HJ(HJ_MAXIMP, s);
+    }
+    __device__ __forceinline__ void joint_v_compute(JV& r) {
+        const float mA = r.mA, iA = r.iA, mB = r.mB, iB = r.iB, exx = r.exx, eyx = r.eyx, eyy = r.eyy, d2 = r.d2, det = r.det;
+        const float jx = r.jx, jy = r.jy, jz = r.jz;
+        const V2 vA = r.vA, vB = r.vB, rA = r.rA, rB = r.rB;
+        float wA = r.wA, wB = r.wB;
+        const int limit = r.limit;
         {   // motor
-            float Cdot = wB - wA - HJ(HJ_MSPEED, s);
-            float impulse = -HJ(HJ_MMASS, s) * Cdot;
-            float oldImpulse = HJ(HJ_MIMP, s);
-            float maxImpulse = HJ(HJ_MAXIMP, s);
+            float Cdot = wB - wA - r.mspeed;
+            float impulse = -r.mmass * Cdot;
+            float oldImpulse = r.mimp;
+            float maxImpulse = r.maximp;
             float ni = clampf(oldImpulse + impulse, -maxImpulse, maxImpulse);
-            if (pred) HJ(HJ_MIMP, s) = ni;
+            r.o_mimp = ni;
             impulse = ni - oldImpulse;
             wA -= iA * impulse; wB += iB * impulse;
         }
@@ -1142,13 +1161,27 @@ public:
         const float jz3 = reduce ? 0.0f : jz + iz;
         // ---- select
         const bool act = limit != 0;
-        if (pred) {
-            HJ(HJ_IMPX, s) = jx + (act ? px : imp2.x);
-            HJ(HJ_IMPY, s) = jy + (act ? py : imp2.y);
-            if (act) HJ(HJ_IMPZ, s) = jz3;
-            HB(HB_VX, a) = act ? vA3.x : vA2.x; HB(HB_VY, a) = act ? vA3.y : vA2.y; HB(HB_W, a) = act ? wA3 : wA2;
-            HB(HB_VX, b) = act ? vB3.x : vB2.x; HB(HB_VY, b) = act ? vB3.y : vB2.y; HB(HB_W, b) = act ? wB3 : wB2;
-        }
+        r.act = act;
+        r.o_jx = jx + (act ? px : imp2.x);
+        r.o_jy = jy + (act ? py : imp2.y);
+        r.o_jz = jz3;
+        r.o_vA = mk(act ? vA3.x : vA2.x, act ? vA3.y : vA2.y); r.o_wA = act ? wA3 : wA2;
+        r.o_vB = mk(act ? vB3.x : vB2.x, act ? vB3.y : vB2.y); r.o_wB = act ? wB3 : wB2;
+    }
+    __device__ __forceinline__ void joint_v_store(int s, const JV& r) {
+        HJ(HJ_MIMP, s) = r.o_mimp;
+        HJ(HJ_IMPX, s) = r.o_jx;
+        HJ(HJ_IMPY, s) = r.o_jy;
+        if (r.act) HJ(HJ_IMPZ, s) = r.o_jz;
+        HB(HB_VX, r.a) = r.o_vA.x; HB(HB_VY, r.a) = r.o_vA.y; HB(HB_W, r.a) = r.o_wA;
+        HB(HB_VX, r.b) = r.o_vB.x; HB(HB_VY, r.b) = r.o_vB.y; HB(HB_W, r.b) = r.o_wB;
+    }
+    __device__ __forceinline__ void joint_solve_velocity(int s) { joint_solve_velocity(s, HJi(HJ_META, s)); }
+    __device__ __forceinline__ void joint_solve_velocity(int s, const int meta) {
+        JV r;
+        joint_v_load(s, meta, r);
+        joint_v_compute(r);
+        joint_v_store(s, r);
     }
     __device__ __forceinline__ bool joint_solve_position(int s) {
         int meta = HJi(PJ_META, s);
@@ -1484,15 +1517,25 @@ public:
                 const int it = T - ((e >> 8) & 0xff);
                 const bool act = e < 0 && it >= 0 && it < vit;
                 const bool isj = act && !(e & SCH_CONTACT), isc = act && (e & SCH_CONTACT);
-                // A slot in which some lane of the warp has a contact: EVERY lane runs the revolute solve and the contact solve
-                // back to back as straight-line code with predicated stores (idle lanes go through the motions on slot 0), so
-                // the two dependency chains overlap instead of being serialised by a divergent branch - the slot takes about
-                // max(joint, contact) instead of their sum, which is what bounds the tick latency of a wide group.
-                if (warp_any_converged(isc)) {
+                // Wide groups (latency-bound launches: tails, small populations): a slot in which some lane of the warp has a
+                // contact runs the revolute solve AND the contact solve in every lane as one straight-line sequence - loads,
+                // both computations, stores (idle lanes go through the motions on slot 0 and store nothing) - so that the two
+                // dependency chains overlap instead of being serialised by a divergent branch: the slot then takes about
+                // max(joint, contact) instead of their sum. Narrow groups are throughput-bound and keep the divergent form.
+                if (gs >= 3 && warp_any_converged(isc)) {
                     // (index word 0 for the idle lanes: bodies 0 / 0, always valid addresses)
-                    joint_solve_velocity(isj ? (e & 0xff) : 0, isj, isj ? meta : 0);
-                    contact_solve_velocity_fused(hot_elem(hc_off, HC_COUNT, isc ? (e & 0xff) : 0), 32, isc, isc ? meta : 0);
-                } else if (isj) joint_solve_velocity(e & 0xff, true, meta);
+                    JV jr; CV cr;
+                    float* hc = hot_elem(hc_off, HC_COUNT, isc ? (e & 0xff) : 0);
+                    joint_v_load(isj ? (e & 0xff) : 0, isj ? meta : 0, jr);
+                    contact_v_load(hc, 32, isc ? meta : 0, cr);
+                    joint_v_compute(jr);
+                    contact_v_compute(cr);
+                    if (isj) joint_v_store(e & 0xff, jr);
+                    if (isc) { contact_v_store1(hc, 32, cr); if (cr.count != 1) contact_v_two(hc, 32, cr); }
+                } else {
+                    if (isj) joint_solve_velocity(e & 0xff, meta);
+                    if (isc) contact_solve_velocity(hot_elem(hc_off, HC_COUNT, e & 0xff), 32);
+                }
                 gsync();
                 pslot = pnext; T = Tnext; e = e_next; meta = meta_next;
             }

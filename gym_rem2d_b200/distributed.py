@@ -64,3 +64,67 @@ def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=Non
     eng = engine() if callable(engine) else engine
     fit, ticks = eng.evaluate(sub, max_ticks)
     return gather_fitness(fit, idx, table.n_creatures, device=device), int(ticks.sum())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Rank 0 drives, the other ranks serve: the evolutionary loop (selection, variation, expansion) runs on rank 0 only; per
+# generation it broadcasts the flattened table, every rank evaluates its shard, the fitness vector is all-gathered.
+_FIELDS = ("body_off", "shape", "hx", "hy", "x0", "y0", "a0", "node_index", "type_ref", "joint_parent", "anchor_a", "anchor_b",
+           "lower", "upper", "max_torque", "ctrl")
+
+
+def broadcast_table(table, src=0, device=None):
+    """Broadcast a PopulationTable from rank ``src`` (``table`` may be None elsewhere). One small header broadcast with the
+    array sizes, then one broadcast per array (the whole table of 65536 creatures is ~45 MB: milliseconds over NVLink)."""
+    import torch
+    import torch.distributed as dist
+    from .flatten import PopulationTable
+    rank = dist.get_rank()
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    ref = {k: None for k in _FIELDS}
+    if rank == src:
+        ref = {k: np.ascontiguousarray(getattr(table, k)) for k in _FIELDS}
+    head = torch.zeros(len(_FIELDS) + 1, dtype=torch.int64, device=dev)
+    if rank == src:
+        head[:-1] = torch.tensor([ref[k].size for k in _FIELDS], dtype=torch.int64)
+        head[-1] = 1 if table is not None else 0
+    dist.broadcast(head, src)
+    if int(head[-1]) == 0:
+        return None                                   # stop signal
+    proto = PopulationTable(*(np.zeros((0, 2) if k in ("anchor_a", "anchor_b") else ((0, 5) if k == "ctrl" else 0),
+                                           dt) for k, dt in zip(_FIELDS, _DTYPES)))
+    out = []
+    for k, dt, n in zip(_FIELDS, _DTYPES, head[:-1].tolist()):
+        if rank == src:
+            t = torch.from_numpy(ref[k].reshape(-1).view(np.uint8)).to(dev)
+        else:
+            t = torch.empty(int(n) * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src)
+        a = t.cpu().numpy().view(dt)
+        shape = getattr(proto, k).shape
+        out.append(a.reshape((-1,) + shape[1:]) if len(shape) > 1 else a)
+    return PopulationTable(*out)
+
+
+_DTYPES = (np.int32, np.uint8, np.float32, np.float32, np.float32, np.float32, np.float32, np.int32, np.int16, np.int16, np.float32,
+           np.float32, np.float32, np.float32, np.float32, np.float64)
+
+
+def evaluate_broadcast(table, engine, max_ticks, device=None):
+    """Collective: rank 0 passes the generation's table (None = stop), the others pass None; everybody returns the fitness of
+    the whole population (or None on stop)."""
+    import torch.distributed as dist
+    table = broadcast_table(table, 0, device)
+    if table is None:
+        return None, 0
+    return evaluate_sharded(table, engine, max_ticks, dist.get_rank(), dist.get_world_size(), device)
+
+
+def serve_evaluations(engine, max_ticks, device=None):
+    """Body of every rank != 0 while rank 0 runs the evolutionary loop: evaluate shards until rank 0 sends the stop signal."""
+    n = 0
+    while True:
+        fit, _ = evaluate_broadcast(None, engine, max_ticks, device)
+        if fit is None:
+            return n
+        n += 1

@@ -77,6 +77,14 @@ def _expand_chunk(args):
     return flatten_population(inds, depth)
 
 
+def _random_chunk(args):
+    """Worker: ``n`` random individuals (REM2D_main.py:296-297 creates the initial population one by one)."""
+    n, module_list, config, seed = args
+    random.seed(seed)
+    np.random.seed(seed % (2 ** 32))
+    return [Individual.random(module_list, config) for _ in range(n)]
+
+
 def _vary_chunk(args):
     """Worker: variation + expansion of one chunk of selected parents (REM2D_main.py:283-290 + evaluate's genome.create).
     Parents arrive pickled (= the deep copy of ``toolbox.clone``); every chunk is seeded so that a run is reproducible
@@ -112,6 +120,7 @@ class run2D:
         self.distributed = distributed       # evaluate this rank's shard and all_gather (torch.distributed must be initialised)
         self.generation_log = []
         self.generation_offset = 0           # generations already done by the run this one resumes
+        self.pipeline_creatures = 16384      # evaluate as soon as this many expanded creatures have arrived (0: no pipelining)
         # persistent workers, started BEFORE any CUDA work of this process (the engine is created lazily, later)
         self.pool = mp.get_context("forkserver").Pool(workers) if workers > 1 else None
 
@@ -144,8 +153,9 @@ class run2D:
         env = self._ensure_env()
         env.seed(K.TERRAIN_SEED)
         if self.distributed:
+            # rank 0 drives the loop and broadcasts the generation's table; the other ranks sit in distributed.serve_evaluations
             from . import distributed as rdist
-            fit, steps = rdist.evaluate_sharded(table, env.engine, self.EVALUATION_STEPS)
+            fit, steps = rdist.evaluate_broadcast(table, env.engine, self.EVALUATION_STEPS)
             return [float(f) for f in fit], steps
         fit = env.evaluate(table=table, steps=self.EVALUATION_STEPS)
         return [float(f) for f in fit], int(env.last_ticks.sum())
@@ -161,6 +171,35 @@ class run2D:
         t2 = time.perf_counter()
         self.last_timing = {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "creature_steps": steps}
         return fit
+
+    def vary_expand_evaluate(self, parents):
+        """One generation's variation, expansion and evaluation, PIPELINED when there is a worker pool and a single device:
+        the workers return (offspring, table) chunk by chunk in order, and as soon as ``pipeline_creatures`` creatures have
+        arrived they are evaluated on the GPU while the workers continue - evaluation hides behind the host-side expansion,
+        which dominates a generation at large population sizes. Returns (offspring, fitness list, timing)."""
+        t0 = time.perf_counter()
+        if self.pool is None or len(parents) < 4 * self.workers or self.distributed or self.pipeline_creatures <= 0:
+            offspring, table = self.vary_and_expand(parents)
+            t1 = time.perf_counter()
+            fit, steps = self.evaluate_table(table)
+            t2 = time.perf_counter()
+            return offspring, fit, {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "evaluate_hidden_s": 0.0, "creature_steps": steps}
+        jobs = [(c, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, random.getrandbits(48))
+                for c in self._chunks(parents)]
+        offspring, fit, pending, n_pending, steps, eval_s = [], [], [], 0, 0, 0.0
+        it = self.pool.imap(_vary_chunk, jobs)
+        for j in range(len(jobs)):
+            off, table = next(it)
+            offspring.extend(off)
+            pending.append(table); n_pending += table.n_creatures
+            if n_pending >= self.pipeline_creatures or j == len(jobs) - 1:
+                te = time.perf_counter()
+                f, s_ = self.evaluate_table(concat(pending) if len(pending) > 1 else pending[0])
+                eval_s += time.perf_counter() - te
+                fit.extend(f); steps += s_
+                pending, n_pending = [], 0
+        total = time.perf_counter() - t0
+        return offspring, fit, {"expand_s": total - eval_s, "evaluate_s": eval_s, "evaluate_hidden_s": eval_s, "creature_steps": steps}
 
     def vary_and_expand(self, parents):
         """clone + mutate + expand: in the workers when there is a pool, else here."""
@@ -203,25 +242,26 @@ class run2D:
             N_GENERATIONS = n_generations
         rank0 = (not self.distributed) or int(os.environ.get("RANK", "0")) == 0
         if population is None:
-            population = [Individual.random(self.moduleList, self.config) for _ in range(self.POPULATION_SIZE)]
+            if self.pool is not None and self.POPULATION_SIZE >= 64 * self.workers:
+                sizes = [len(c) for c in self._chunks(list(range(self.POPULATION_SIZE)))]
+                parts = self.pool.map(_random_chunk, [(n, self.moduleList, self.config, random.getrandbits(48)) for n in sizes])
+                population = [ind for part in parts for ind in part]
+            else:
+                population = [Individual.random(self.moduleList, self.config) for _ in range(self.POPULATION_SIZE)]
             for ind, fit in zip(population, self.evaluate_batch(population)):
                 ind.fitness = fit
         for i in range(N_GENERATIONS):
             g = self.generation_offset + i                     # absolute generation index (file suffix)
             t0 = time.perf_counter()
             parents = selTournament(population, len(population), tournsize=4)
-            offspring, table = self.vary_and_expand(parents)
-            t1 = time.perf_counter()
-            fitness_values, steps = self.evaluate_table(table)
-            t2 = time.perf_counter()
+            offspring, fitness_values, timing = self.vary_expand_evaluate(parents)
             for ind, fit in zip(offspring, fitness_values):
                 ind.fitness = fit
             population = offspring                                   # no elitism, like the reference
             self.EVALUATION_NR += len(population)
             self.fitnessData.addFitnessData(fitness_values, g + 1)
             self.generation_log.append({"generation": g + 1, "min": float(np.min(fitness_values)), "max": float(np.max(fitness_values)),
-                                        "mean": float(np.mean(fitness_values)), "seconds": time.perf_counter() - t0,
-                                        "expand_s": t1 - t0, "evaluate_s": t2 - t1, "creature_steps": steps})
+                                        "mean": float(np.mean(fitness_values)), "seconds": time.perf_counter() - t0, **timing})
             if self.SAVEDATA and rank0:
                 if g % self.CHECKPOINT_FREQUENCY == 0 or i == N_GENERATIONS - 1:     # the last generation is always saved
                     self._checkpoint(population, g)
