@@ -120,7 +120,11 @@ class run2D:
         self.distributed = distributed       # evaluate this rank's shard and all_gather (torch.distributed must be initialised)
         self.generation_log = []
         self.generation_offset = 0           # generations already done by the run this one resumes
-        self.pipeline_creatures = 16384      # evaluate as soon as this many expanded creatures have arrived (0: no pipelining)
+        # evaluate as soon as this many expanded creatures have arrived (0: expand everything, then evaluate once). Off by
+        # default: measured at population 65536 with 14 workers on a 16-core box, the evaluation's host thread (it polls the park
+        # counters and launches the tail kernels) is starved by the busy workers and the chunked evaluations take 6-8 s per
+        # generation instead of 1 s for one evaluation of the whole table (profiles/r2_ea_config5.json)
+        self.pipeline_creatures = 0
         # persistent workers, started BEFORE any CUDA work of this process (the engine is created lazily, later)
         self.pool = mp.get_context("forkserver").Pool(workers) if workers > 1 else None
 

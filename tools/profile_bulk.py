@@ -1,10 +1,11 @@
 """Workload for the ncu --set full capture of the dominant launch: the bulk launch of the largest class (NB=22) of the
-bench population. Parking is disabled so that every evaluation is exactly one episode_kernel launch per class
-(launch order: largest class first)."""
+bench population in the PRODUCTION configuration (parking on: the first episode_kernel launch of an evaluation is the queue-mode
+launch of the largest class; tail launches follow). `nopark` as second argument disables parking (one launch per class)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, ".")
-os.environ["REM2D_PARK_TICKS"] = "0"
+if len(sys.argv) > 2 and sys.argv[2] == "nopark":
+    os.environ["REM2D_PARK_TICKS"] = "0"
 from gym_rem2d_b200 import constants as K, terrain
 from gym_rem2d_b200.capi import Engine
 from gym_rem2d_b200.population import random_population

@@ -23,7 +23,11 @@ xs, ys = terrain.generate_terrain()
 o = OracleEngine(threads=os.cpu_count() or 8)
 o.set_terrain(ys, K.TERRAIN_STEP)
 fo, to = o.evaluate(pop, max_ticks)
-for name, env in (("bulk+tail", {"REM2D_WARP_MODE_MAX": "0", "REM2D_SMEM_BUDGET_KB": "8", "REM2D_PARK_TICKS": "60", "REM2D_PARK_CAP": "0.25"}),
+for name, env in (("queue G=1 + refill + tail G=32", {"REM2D_WARP_MODE_MAX": "0", "REM2D_GROUP_SHIFT": "0", "REM2D_SMEM_BUDGET_KB": "8",
+                                                      "REM2D_PARK_TICKS": "60", "REM2D_PARK_CAP": "0.25"}),
+                  ("queue G=4 + refill + tail G=8", {"REM2D_WARP_MODE_MAX": "0", "REM2D_GROUP_SHIFT": "2", "REM2D_SMEM_BUDGET_KB": "8",
+                                                     "REM2D_PARK_TICKS": "60", "REM2D_PARK_CAP": "0.25", "REM2D_TAIL_GROUP_SHIFT": "3"}),
+                  ("automatic group width (under-filled GPU)", {"REM2D_WARP_MODE_MAX": "0"}),
                   ("warp-per-creature", {"REM2D_WARP_MODE_MAX": "1000000"})):
     os.environ.update(env)
     g = Engine(device=0)
