@@ -27,6 +27,9 @@
 struct ParkPolicy {
     int ticks;        // park a creature that is still alive after this many ticks (0: never park)
     int cap;          // at most this many creatures of the class are parked
+    float lead_x;     // > 0: a creature whose root has reached x >= lead_x (after lead_from ticks) is parked at once: the wall of death
+    int lead_from;    //   needs ticks/wod_speed ticks to get there, so the creature would reach the tick threshold anyway - it just
+                      //   moves to the low-latency launches sooner (the long-lived creatures bound the makespan)
     int late_from;    // creatures pulled from this position of the class queue on (= after the first round) are late starters:
     int late_ticks;   //   they park after late_ticks ticks - they bound the makespan, so they move to the low-latency launches sooner
     // diagnostics (trace option): every 4th tick lane 0 of each warp records {globaltimer us, live creatures | tick << 8 |

@@ -163,6 +163,9 @@ struct Options {
     int park_ticks = -1;         // park threshold of the queue mode (-1: automatic, 0: never park)
     double park_cap = -1.0;      // fraction of a class that may be parked (-1: automatic)
     int park_late_ticks = -1;    // park threshold of creatures pulled after the first round (-1: same as park_ticks)
+    int park_lead = 0;           // park a creature as soon as its root is where the wall of death will be at the park threshold.
+                                 // Measured and rejected as default: more creatures are parked, and early, while the GPU is still full -
+                                 // the tail launches wait 100-300 ms for resources (950-1200 ms against 800 ms)
     double smem_budget_kb = 227.0, small_weight = 1.0;
     int min_class = 0;
     int group_shift = -1;        // log2 lanes per creature in the queue / step kernels (-1: per class default)
@@ -201,6 +204,7 @@ struct rem2d_handle {
     // population
     int n_creatures = 0, n_bodies = 0, n_joints = 0;
     std::vector<int32_t> body_off;
+    std::vector<float> priority;         // rem2d_set_priority: expected lifetimes for the next upload (empty: none)
     std::vector<int> creature_class, creature_lane;     // lane index within the class (batch*32+lane)
     Buf d_pop_mem[16];
     Buf b_results, b_roots;
@@ -246,6 +250,7 @@ static bool set_option(Options& o, const char* name, double v) {
     else if (n == "park_ticks") o.park_ticks = (int)v;
     else if (n == "park_cap") o.park_cap = v;
     else if (n == "park_late_ticks") o.park_late_ticks = (int)v;
+    else if (n == "park_lead") o.park_lead = (int)v;
     else if (n == "smem_budget_kb") o.smem_budget_kb = v;
     else if (n == "small_weight") o.small_weight = v;
     else if (n == "min_class") o.min_class = std::max(0, std::min(N_CLASSES - 1, (int)v));
@@ -259,7 +264,7 @@ static bool set_option(Options& o, const char* name, double v) {
     return true;
 }
 static void options_from_env(Options& o) {
-    static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "park_late_ticks", "smem_budget_kb", "small_weight", "min_class",
+    static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "park_late_ticks", "park_lead", "smem_budget_kb", "small_weight", "min_class",
                                   "group_shift", "tail_group_shift", "second_group_shift", "trace"};
     for (const char* n : names) {
         std::string env = "REM2D_";
@@ -587,8 +592,12 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
     for (int k = 0; k < N_CLASSES; ++k) {
         auto& m = members[k];
         if (m.empty()) continue;
-        // big creatures first: batches of similar size limit lane divergence, and the costly batches start early
+        // big creatures first: batches of similar size limit lane divergence, and the costly batches start early; creatures
+        // the caller expects to be long-lived (rem2d_set_priority) go to the very front of the class queue
+        const bool prio = (int)h->priority.size() == n;
         std::stable_sort(m.begin(), m.end(), [&](int a, int b) {
+            const int la = prio && h->priority[a] >= 130.0f, lb = prio && h->priority[b] >= 130.0f;
+            if (la != lb) return la > lb;
             return (pop->body_off[a + 1] - pop->body_off[a]) > (pop->body_off[b + 1] - pop->body_off[b]);
         });
         ClassState& cs = h->cls[k];
@@ -627,6 +636,7 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
     }
     h->h_fitness.assign(n, 0.0); h->h_ticks.assign(n, 0); h->h_alive.assign(n, 0); h->h_status.assign(n, 0);
     h->have_pop = true;
+    h->priority.clear();                 // the hint applies to one upload
     return do_reset ? launch_reset(h) : REM2D_OK;
 }
 
@@ -705,7 +715,7 @@ static int promote_overflowed(rem2d_handle* h, int max_ticks) {
             CK(cudaMemsetAsync(d_queue, 0, sizeof(int), h->user_stream));
             g_classes(k).episode(h->image, gs, grid, h->user_stream, (float*)cs.b_redo_slots.p, d_order, (int)redo[k].size(), d_queue, h->dpop, h->d_ter,
                                  h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                                 ParkPolicy{0, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr, 1);
+                                 ParkPolicy{0, 0, 0.0f, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr, 1);
             h->launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->user_stream));      // redo[] (pageable source of the copy) goes out of scope
@@ -839,7 +849,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         if (warp_mode) {      // queue mode with a whole warp per creature and one warp for every creature
             g_classes(k).episode(1, 5, cs.n_members, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop, h->d_ter,
                                  h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                                 ParkPolicy{0, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr, 1);
+                                 ParkPolicy{0, 0, 0.0f, 0, 0, 0, nullptr, nullptr}, nullptr, nullptr, nullptr, 1);
             CK(cudaEventRecord(cs.t_end, cs.stream));
             h->launches++;
             continue;
@@ -851,6 +861,9 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         park.cap = std::min(cs.n_members, std::max(32, std::min((int)(h->n_sms * 64 * cap_frac), (int)(cs.n_members * cap_frac))));
         // late starters (pulled when a lane of the first round frees up): park right after the wall of death has passed the
         // start pad (tick 126), so that the long-lived ones among them continue at the tail launches' tick latency
+        // a root that is already where the wall of death will be at the park threshold survives until then unless it walks back
+        park.lead_x = (h->opt.park_lead && h->cfg.terminate) ? (float)(park.ticks * h->cfg.wod_speed) : 0.0f;
+        park.lead_from = 32;
         park.late_from = cs.episode_grid * (32 >> class_gs(h, k));
         park.late_ticks = h->opt.park_late_ticks >= 0 ? std::min(h->opt.park_late_ticks, park.ticks) : park.ticks;
         park.trace = nullptr; park.tail_trace = nullptr;
@@ -934,7 +947,10 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
                 if (cnt > launched[k]) ++waited[k]; else waited[k] = 0;
                 if (cnt > launched[k] && (finished_now[k] || cnt - launched[k] >= 4 || waited[k] >= 3)) {
                     waited[k] = 0;
-                    g_classes(k).tail(h->image, h->opt.tail_group_shift, idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
+                    // a handful of parked creatures (random populations): a warp each; dozens at once (evolved populations,
+                    // where many creatures outlive the threshold): 8 lanes each - 4x fewer warps at nearly the same tick latency
+                    const int tail_gs = (cnt - launched[k] >= 32) ? std::min(3, h->opt.tail_group_shift) : h->opt.tail_group_shift;
+                    g_classes(k).tail(h->image, tail_gs, idle_stream(), cs.d_state2, cs.d_lc_work[0], launched[k], cnt - launched[k],
                                       h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
                                       trace ? (unsigned int*)cs.b_ttrace.p : nullptr);
                     CK(cudaGetLastError());
@@ -1151,6 +1167,13 @@ int rem2d_debug_tail_trace(rem2d_handle* h, int k, unsigned int* out, int64_t ma
     if ((int64_t)words > max_words) words = (size_t)max_words;
     CK(cudaMemcpy(out, cs.b_ttrace.p, words * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     return parked;
+}
+
+int rem2d_set_priority(rem2d_handle* h, const float* expected_ticks, int32_t n) {
+    if (!h || n < 0) return REM2D_E_INVALID;
+    if (!expected_ticks || n == 0) h->priority.clear();
+    else h->priority.assign(expected_ticks, expected_ticks + n);
+    return REM2D_OK;
 }
 
 int rem2d_read_roots(rem2d_handle* h, float* root_x, double* wod, int32_t* alive) {

@@ -573,7 +573,8 @@ public:
             AUX(b) = w;
         }
         special = group_any(special);
-        has = group_any(has);                 // (also the barrier that publishes the scratch words)
+        has = group_any(has);
+        gsync();                              // publishes the scratch words
         if (leader()) {
             if (special) find_new_contacts();
             else if (has) {
@@ -796,7 +797,8 @@ public:
             if (!overlap_edge(key_edge(key), b)) { setCi(CF_KEY, i, key | CK_DESTROY_MARK); marked = true; continue; }
             contact_update(i);
         }
-        if (group_any(marked)) {          // (group_any is a group barrier as well)
+        if (group_any(marked)) {
+            gsync();                      // (a vote synchronises the lanes but is not a memory barrier)
             if (leader())
                 for (int i = nc - 1; i >= 0; --i)
                     if (Ci(CF_KEY, i) & CK_DESTROY_MARK) destroy_contact(i);
@@ -951,13 +953,15 @@ public:
     // a two-point manifold continues from the post-friction velocity in contact_v_two. Every path performs exactly the
     // operations of contact_solve_velocity.
     struct CV { int b, count; float mB, iB, wB, tm0, ti0, ni0, nm0, o_ti0, o_ni0, wF, w1; V2 vB, normal, tangent, r0, vF, v1; };
-    __device__ __forceinline__ void contact_v_load(const float* hc, const int st, const int meta, CV& c) {
+    // (`on` = false: an idle lane of a fused slot - it computes on zeros and neither loads nor stores)
+    #define LDP(x) (on ? (x) : 0.0f)
+    __device__ __forceinline__ void contact_v_load(const float* hc, const int st, const int meta, CV& c, const bool on = true) {
         c.b = meta & 0xff; c.count = (meta >> 8) & 3;
-        c.mB = HB(HB_INVM, c.b); c.iB = HB(HB_INVI, c.b);
-        c.vB = mk(HB(HB_VX, c.b), HB(HB_VY, c.b)); c.wB = HB(HB_W, c.b);
-        c.normal = mk(hc[HC_NX * st], hc[HC_NY * st]); c.tangent = cross_vs(c.normal, 1.0f);
-        c.r0 = mk(hc[HC_R0X * st], hc[HC_R0Y * st]);
-        c.tm0 = hc[HC_TM0 * st]; c.ti0 = hc[HC_TI0 * st]; c.ni0 = hc[HC_NI0 * st]; c.nm0 = hc[HC_NM0 * st];
+        c.mB = LDP(HB(HB_INVM, c.b)); c.iB = LDP(HB(HB_INVI, c.b));
+        c.vB = mk(LDP(HB(HB_VX, c.b)), LDP(HB(HB_VY, c.b))); c.wB = LDP(HB(HB_W, c.b));
+        c.normal = mk(LDP(hc[HC_NX * st]), LDP(hc[HC_NY * st])); c.tangent = cross_vs(c.normal, 1.0f);
+        c.r0 = mk(LDP(hc[HC_R0X * st]), LDP(hc[HC_R0Y * st]));
+        c.tm0 = LDP(hc[HC_TM0 * st]); c.ti0 = LDP(hc[HC_TI0 * st]); c.ni0 = LDP(hc[HC_NI0 * st]); c.nm0 = LDP(hc[HC_NM0 * st]);
     }
     __device__ __forceinline__ void contact_v_compute(CV& c) {
         const float friction = k->friction;
@@ -1106,16 +1110,16 @@ public:
     // Loads / arithmetic / stores of the solve as separate pieces (see CV above for why).
     struct JV { int a, b, limit; bool act; float mA, iA, mB, iB, wA, wB, exx, eyx, eyy, d2, det, jx, jy, jz, mspeed, mmass, mimp, maximp;
                 float o_mimp, o_jx, o_jy, o_jz, o_wA, o_wB; V2 vA, vB, rA, rB, o_vA, o_vB; };
-    __device__ __forceinline__ void joint_v_load(int s, const int meta, JV& r) {
+    __device__ __forceinline__ void joint_v_load(int s, const int meta, JV& r, const bool on = true) {
         r.a = meta & 0xff; r.b = (meta >> 8) & 0xff; r.limit = (meta >> 16) & 3;
-        r.mA = HB(HB_INVM, r.a); r.iA = HB(HB_INVI, r.a); r.mB = HB(HB_INVM, r.b); r.iB = HB(HB_INVI, r.b);
-        r.vA = mk(HB(HB_VX, r.a), HB(HB_VY, r.a)); r.wA = HB(HB_W, r.a);
-        r.vB = mk(HB(HB_VX, r.b), HB(HB_VY, r.b)); r.wB = HB(HB_W, r.b);
-        r.rA = mk(HJ(HJ_RAX, s), HJ(HJ_RAY, s)); r.rB = mk(HJ(HJ_RBX, s), HJ(HJ_RBY, s));
-        r.exx = HJ(HJ_EXX, s); r.eyx = HJ(HJ_EYX, s); r.eyy = HJ(HJ_EYY, s);
-        r.d2 = HJ(HJ_INV2, s); r.det = HJ(HJ_INV3, s);
-        r.jx = HJ(HJ_IMPX, s); r.jy = HJ(HJ_IMPY, s); r.jz = HJ(HJ_IMPZ, s);
-        r.mspeed = HJ(HJ_MSPEED, s); r.mmass = HJ(HJ_MMASS, s); r.mimp = HJ(HJ_MIMP, s); r.maximp = HJ(HJ_MAXIMP, s);
+        r.mA = LDP(HB(HB_INVM, r.a)); r.iA = LDP(HB(HB_INVI, r.a)); r.mB = LDP(HB(HB_INVM, r.b)); r.iB = LDP(HB(HB_INVI, r.b));
+        r.vA = mk(LDP(HB(HB_VX, r.a)), LDP(HB(HB_VY, r.a))); r.wA = LDP(HB(HB_W, r.a));
+        r.vB = mk(LDP(HB(HB_VX, r.b)), LDP(HB(HB_VY, r.b))); r.wB = LDP(HB(HB_W, r.b));
+        r.rA = mk(LDP(HJ(HJ_RAX, s)), LDP(HJ(HJ_RAY, s))); r.rB = mk(LDP(HJ(HJ_RBX, s)), LDP(HJ(HJ_RBY, s)));
+        r.exx = LDP(HJ(HJ_EXX, s)); r.eyx = LDP(HJ(HJ_EYX, s)); r.eyy = LDP(HJ(HJ_EYY, s));
+        r.d2 = LDP(HJ(HJ_INV2, s)); r.det = LDP(HJ(HJ_INV3, s));
+        r.jx = LDP(HJ(HJ_IMPX, s)); r.jy = LDP(HJ(HJ_IMPY, s)); r.jz = LDP(HJ(HJ_IMPZ, s));
+        r.mspeed = LDP(HJ(HJ_MSPEED, s)); r.mmass = LDP(HJ(HJ_MMASS, s)); r.mimp = LDP(HJ(HJ_MIMP, s)); r.maximp = LDP(HJ(HJ_MAXIMP, s));
     }
     __device__ __forceinline__ void joint_v_compute(JV& r) {
         const float mA = r.mA, iA = r.iA, mB = r.mB, iB = r.iB, exx = r.exx, eyx = r.eyx, eyy = r.eyy, d2 = r.d2, det = r.det;
@@ -1481,6 +1485,7 @@ public:
             if (maxdeg > P) P = maxdeg;
         }
         P = bcast(P);
+        gsync();
         for (;;) {
             if (P > RB_SCHED_ROWS) { P = 0; break; }
             for (int q = 0; q < P; ++q) SCH(q, sub) = 0;
@@ -1491,6 +1496,7 @@ public:
             ok = bcast(ok);
             if (ok) { sched_smax = bcast(smax); break; }
             ++P;
+            gsync();
         }
         sched_P = P;
         gsync();
@@ -1519,15 +1525,15 @@ public:
                 const bool isj = act && !(e & SCH_CONTACT), isc = act && (e & SCH_CONTACT);
                 // Wide groups (latency-bound launches: tails, small populations): a slot in which some lane of the warp has a
                 // contact runs the revolute solve AND the contact solve in every lane as one straight-line sequence - loads,
-                // both computations, stores (idle lanes go through the motions on slot 0 and store nothing) - so that the two
+                // both computations, stores (idle lanes compute on zeros: their loads and stores are predicated off) - so that the two
                 // dependency chains overlap instead of being serialised by a divergent branch: the slot then takes about
                 // max(joint, contact) instead of their sum. Narrow groups are throughput-bound and keep the divergent form.
                 if (gs >= 3 && warp_any_converged(isc)) {
                     // (index word 0 for the idle lanes: bodies 0 / 0, always valid addresses)
                     JV jr; CV cr;
                     float* hc = hot_elem(hc_off, HC_COUNT, isc ? (e & 0xff) : 0);
-                    joint_v_load(isj ? (e & 0xff) : 0, isj ? meta : 0, jr);
-                    contact_v_load(hc, 32, isc ? meta : 0, cr);
+                    joint_v_load(isj ? (e & 0xff) : 0, isj ? meta : 0, jr, isj);
+                    contact_v_load(hc, 32, isc ? meta : 0, cr, isc);
                     joint_v_compute(jr);
                     contact_v_compute(cr);
                     if (isj) joint_v_store(e & 0xff, jr);

@@ -172,7 +172,8 @@ static __device__ __forceinline__ void episode_body(const Layout& L, int gs, int
                 // its partial work must not be counted
                 if (st) sim.cnt = snapshot;
                 my = -1;
-            } else if (!tail && park.ticks > 0 && t >= park_at) {
+            } else if (!tail && park.ticks > 0 &&
+                       (t >= park_at || (park.lead_x > 0.0f && t >= park.lead_from && sim.B(BF_CX, 0) >= park.lead_x))) {
                 // long-lived creature: park its state; the latency-oriented tail mode (one warp per creature) finishes it.
                 // (the counter never exceeds the cap: the host hands every counted slot to a tail launch)
                 int slot = -1;
@@ -255,7 +256,7 @@ int rem2d_episode_blocks_per_sm(int image, int dyn_smem_bytes) {
 void rem2d_launch_tail(const Layout& L, int image, int gs, cudaStream_t st, float* park_state, int* park_creature, int first_slot, int n_parked,
                        const Terrain* ter, const Consts* k, int max_ticks, double* fitness, int* ticks, int* alive, int* status,
                        unsigned long long* counters, unsigned int* tail_trace) {
-    ParkPolicy none = {0, 0, 0, 0, nullptr, tail_trace};
+    ParkPolicy none = {0, 0, 0.0f, 0, 0, 0, nullptr, tail_trace};
     const int per = 32 >> gs, grid = (n_parked + per - 1) / per, smem = make_hot_layout(L, gs).rows * 128;
     if (image) episode_kernel_r128<<<grid, 32, smem, st>>>(L, gs, 1, nullptr, nullptr, 0, nullptr, DevPop(), ter, k, max_ticks, fitness, ticks,
                                                             alive, status, counters, none, park_state, park_creature, nullptr, first_slot,

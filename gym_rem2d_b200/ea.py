@@ -120,13 +120,19 @@ class run2D:
         self.distributed = distributed       # evaluate this rank's shard and all_gather (torch.distributed must be initialised)
         self.generation_log = []
         self.generation_offset = 0           # generations already done by the run this one resumes
+        self.expected_ticks = None           # scheduling hint for the next evaluation (parents' lifetimes)
+        self.last_lifetimes = None
         # evaluate as soon as this many expanded creatures have arrived (0: expand everything, then evaluate once). Off by
         # default: measured at population 65536 with 14 workers on a 16-core box, the evaluation's host thread (it polls the park
         # counters and launches the tail kernels) is starved by the busy workers and the chunked evaluations take 6-8 s per
         # generation instead of 1 s for one evaluation of the whole table (profiles/r2_ea_config5.json)
         self.pipeline_creatures = 0
         # persistent workers, started BEFORE any CUDA work of this process (the engine is created lazily, later)
-        self.pool = mp.get_context("forkserver").Pool(workers) if workers > 1 else None
+        # (forkserver re-imports __main__ in the workers, which an interactive / stdin main cannot offer: plain fork there - still
+        # before any CUDA work of this process)
+        import sys
+        method = "forkserver" if getattr(sys.modules.get("__main__"), "__file__", None) else "fork"
+        self.pool = mp.get_context(method).Pool(workers) if workers > 1 else None
 
     def close(self):
         if self.pool is not None:
@@ -161,7 +167,10 @@ class run2D:
             from . import distributed as rdist
             fit, steps = rdist.evaluate_broadcast(table, env.engine, self.EVALUATION_STEPS)
             return [float(f) for f in fit], steps
+        if self.expected_ticks is not None and len(self.expected_ticks) == table.n_creatures and hasattr(env, "engine"):
+            env.engine.set_priority(self.expected_ticks)        # offspring are expected to live about as long as their parents
         fit = env.evaluate(table=table, steps=self.EVALUATION_STEPS)
+        self.last_lifetimes = np.asarray(env.last_ticks)
         return [float(f) for f in fit], int(env.last_ticks.sum())
 
     def evaluate_batch(self, individuals):
@@ -258,9 +267,12 @@ class run2D:
             g = self.generation_offset + i                     # absolute generation index (file suffix)
             t0 = time.perf_counter()
             parents = selTournament(population, len(population), tournsize=4)
+            self.expected_ticks = np.array([getattr(p, "lifetime", 0) for p in parents], np.float32)
             offspring, fitness_values, timing = self.vary_expand_evaluate(parents)
-            for ind, fit in zip(offspring, fitness_values):
+            for k, (ind, fit) in enumerate(zip(offspring, fitness_values)):
                 ind.fitness = fit
+                if self.last_lifetimes is not None and len(self.last_lifetimes) == len(offspring):
+                    ind.lifetime = int(self.last_lifetimes[k])
             population = offspring                                   # no elitism, like the reference
             self.EVALUATION_NR += len(population)
             self.fitnessData.addFitnessData(fitness_values, g + 1)

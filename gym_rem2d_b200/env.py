@@ -34,8 +34,8 @@ class _Box:
 class BatchedModular2D:
     """A whole population of creatures, each in its own world, stepped together on one GPU."""
 
-    def __init__(self, device=0, stream=None, max_perturbance=K.MAX_PERTURBANCE_TERRAIN, lib_path=None, **config):
-        self.engine = Engine(lib_path=lib_path, device=device, stream=stream, **config)
+    def __init__(self, device=0, stream=None, max_perturbance=K.MAX_PERTURBANCE_TERRAIN, lib_path=None, precision="exact", **config):
+        self.engine = Engine(lib_path=lib_path, device=device, stream=stream, precision=precision, **config)
         self.max_perturbance = max_perturbance
         self.table = None
         self.seed(K.TERRAIN_SEED)

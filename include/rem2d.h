@@ -170,6 +170,12 @@ int64_t rem2d_launch_count(rem2d_handle* h);
  * "smem_budget_kb", "small_weight", "min_class", "group_shift", "tail_group_shift", "trace", "phased" (DESIGN.md section 4).
  * Unknown names return REM2D_E_INVALID. The oracle accepts the same names and ignores them. */
 int rem2d_set_option(rem2d_handle* h, const char* name, double value);
+/* Optional scheduling hint for the NEXT rem2d_upload / rem2d_evaluate: expected lifetime of every creature in ticks (an EA passes
+ * the lifetime of the parent). Creatures expected to outlive the wall of death's arrival at the start pad (>= 130 ticks) are
+ * started first, so that the sequential ticks of the long-lived creatures - which bound the run time of a generation - overlap
+ * the bulk instead of following it (the multiprocessing.Pool of REM2D_main.py:256-262 has the same problem with its static chunks).
+ * Never changes results. n must equal the population size of the next upload, otherwise the hint is dropped; NULL clears it. */
+int rem2d_set_priority(rem2d_handle* h, const float* expected_ticks, int32_t n);
 /* Cheap per-creature read-out for step-wise drivers (what Modular2D.step needs to form its reward, Modular2DEnv.py:642-649):
  * root x (= robot.components[0].position[0]), wall-of-death position, alive flag. Any pointer may be NULL. Valid after
  * rem2d_upload / rem2d_reset / rem2d_step. */

@@ -17,7 +17,7 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(rem2d_[a-z0-9_]+)\s*\(", src)))
 
 
-@pytest.mark.parametrize("lib", [capi.CUDA_LIB, os.path.join(ROOT, "oracle", "librem2d_oracle.so")])
+@pytest.mark.parametrize("lib", [capi.CUDA_LIB, capi.CUDA_LIB_FAST, os.path.join(ROOT, "oracle", "librem2d_oracle.so")])
 def test_library_exports_every_declared_symbol(lib):
     if not os.path.exists(lib):
         import __graft_entry__ as g

@@ -329,3 +329,37 @@ def test_set_option_and_read_roots():
     assert np.array_equal(xg, xo) and np.array_equal(wg, wo) and np.array_equal(ag, ao)
     root = pop.body_off[:-1]
     assert np.array_equal(xg, g.read_state()["pose"][root, 0])
+
+
+def test_priority_hint_changes_the_schedule_not_the_results():
+    from gym_rem2d_b200.population import random_population
+    pop = random_population(2048, ("lsystem",), seed=97, workers=4)
+    xs, ys = terrain.generate_terrain()
+    fo, to, co = _oracle_eval(pop, ys)
+    g = Engine(device=0)
+    g.set_option("warp_mode_max", 0); g.set_option("group_shift", 0); g.set_option("smem_budget_kb", 20)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    g.set_priority(to.astype(np.float32))            # a perfect hint: the real lifetimes
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo) and g.counters() == co
+    g.set_priority(np.random.RandomState(0).uniform(0, 400, pop.n_creatures))      # a useless one
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, to) and np.array_equal(fg, fo)
+
+
+def test_fast_precision_build_keeps_the_fitness_distribution():
+    """Engine(precision="fast") = the same kernels compiled with fused multiply-adds: not bit-identical any more (individual
+    trajectories diverge chaotically after contact events), judged on the fitness distribution of whole episodes."""
+    from gym_rem2d_b200.population import random_population
+    from tests.test_fitness_distribution import ks_statistic
+    pop = random_population(4096, ("lsystem",), seed=2, workers=4)
+    xs, ys = terrain.generate_terrain()
+    res = {}
+    for precision in ("exact", "fast"):
+        g = Engine(device=0, precision=precision)
+        g.set_terrain(ys, K.TERRAIN_STEP)
+        res[precision] = g.evaluate(pop, K.EVALUATION_STEPS)
+    (fe, te), (ff, tf) = res["exact"], res["fast"]
+    assert not np.array_equal(fe, ff)                       # it really is a different arithmetic
+    assert ks_statistic(fe, ff) <= 0.02 and abs(fe.mean() - ff.mean()) <= 0.01
+    assert np.mean(te == tf) >= 0.9

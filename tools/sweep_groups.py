@@ -21,8 +21,11 @@ for cfg in configs:
     for k_, v_ in env.items():
         os.environ[k_] = v_
     lib = env.pop("LIB", None)
+    prio = env.pop("PRIO", None)
     g = Engine(device=0, lib_path=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gym_rem2d_b200", "csrc", lib) if lib else None)
     g.set_terrain(ys, K.TERRAIN_STEP)
+    if prio and ref is not None:
+        g.set_priority(ref[1].astype(np.float32))      # a perfect lifetime hint (what an EA approximates with the parents' lifetimes)
     g.upload(pop)
     ms = []
     for i in range(3):
