@@ -16,8 +16,8 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB = os.environ.get("REM2D_CUDA_LIB") or os.path.join(HERE, "csrc", "librem2d_cuda.so")   # env override: A/B builds
-# opt-in build with fused multiply-adds: ~1.27x faster, NOT bit-identical to the oracle (fitness distribution unchanged: KS 0.002,
-# profiles/r2_fma.txt). Engine(precision="fast") selects it; the default is the exact library.
+# optional build with fused multiply-adds (`make -C gym_rem2d_b200/csrc fast`): NOT bit-identical to the oracle, fitness distribution
+# unchanged (KS 0.002), 1.06x on the bench population (profiles/r2_fma.txt). Engine(precision="fast") selects it; default = exact.
 CUDA_LIB_FAST = os.path.join(HERE, "csrc", "librem2d_cuda_fma.so")
 
 N_COUNTERS = 12

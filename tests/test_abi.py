@@ -19,6 +19,8 @@ def declared_symbols():
 
 @pytest.mark.parametrize("lib", [capi.CUDA_LIB, capi.CUDA_LIB_FAST, os.path.join(ROOT, "oracle", "librem2d_oracle.so")])
 def test_library_exports_every_declared_symbol(lib):
+    if lib == capi.CUDA_LIB_FAST and not os.path.exists(lib):
+        pytest.skip("optional fast-precision build not present (make -C gym_rem2d_b200/csrc fast)")
     if not os.path.exists(lib):
         import __graft_entry__ as g
         g.build()

@@ -350,8 +350,11 @@ def test_priority_hint_changes_the_schedule_not_the_results():
 def test_fast_precision_build_keeps_the_fitness_distribution():
     """Engine(precision="fast") = the same kernels compiled with fused multiply-adds: not bit-identical any more (individual
     trajectories diverge chaotically after contact events), judged on the fitness distribution of whole episodes."""
+    from gym_rem2d_b200 import capi
     from gym_rem2d_b200.population import random_population
     from tests.test_fitness_distribution import ks_statistic
+    if not __import__("os").path.exists(capi.CUDA_LIB_FAST):
+        pytest.skip("optional fast-precision build not present (make -C gym_rem2d_b200/csrc fast)")
     pop = random_population(4096, ("lsystem",), seed=2, workers=4)
     xs, ys = terrain.generate_terrain()
     res = {}
