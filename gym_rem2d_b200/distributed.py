@@ -82,12 +82,12 @@ def broadcast_table(table, src=0, device=None):
     rank = dist.get_rank()
     dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
     ref = {k: None for k in _FIELDS}
-    if rank == src:
+    if rank == src and table is not None:
         ref = {k: np.ascontiguousarray(getattr(table, k)) for k in _FIELDS}
     head = torch.zeros(len(_FIELDS) + 1, dtype=torch.int64, device=dev)
-    if rank == src:
+    if rank == src and table is not None:
         head[:-1] = torch.tensor([ref[k].size for k in _FIELDS], dtype=torch.int64)
-        head[-1] = 1 if table is not None else 0
+        head[-1] = 1
     dist.broadcast(head, src)
     if int(head[-1]) == 0:
         return None                                   # stop signal

@@ -66,3 +66,43 @@ def test_two_ranks_gloo_gather_equals_single_rank():
         fit, steps = ret[r]
         assert np.array_equal(fit, ref.astype(np.float32))      # bitwise identical, any shard count
     assert ret[0][1] + ret[1][1] == int(ticks.sum())
+
+
+def _serve_worker(rank, world, port, table, ys, ret):
+    """rank 0 drives two 'generations' (table broadcast + sharded evaluation + fitness gather) and sends the stop signal; the other
+    rank sits in serve_evaluations - the multi-GPU form of the EA loop (ea.run2D(distributed=True) / bench.py --ea)."""
+    import torch.distributed as dist
+    from gym_rem2d_b200 import distributed as rdist
+    from oracle.oracle import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    e = OracleEngine()
+    e.set_terrain(ys, K.TERRAIN_STEP)
+    if rank == 0:
+        out = []
+        for gen in range(2):
+            sub = table if gen == 0 else table.select(np.arange(table.n_creatures)[::-1].copy())
+            fit, steps = rdist.evaluate_broadcast(sub, e, 300)
+            out.append(fit)
+        assert rdist.broadcast_table(None, 0) is None          # stop signal
+        ret[0] = out
+    else:
+        ret[rank] = rdist.serve_evaluations(e, 300)
+    dist.destroy_process_group()
+
+
+def test_rank0_drives_and_the_other_ranks_serve():
+    random.seed(6)
+    table = flatten_population([Individual.random(encoding="lsystem") for _ in range(29)])
+    xs, ys = terrain.generate_terrain()
+    from oracle.oracle import OracleEngine
+    e = OracleEngine()
+    e.set_terrain(ys, K.TERRAIN_STEP)
+    ref, _ = e.evaluate(table, 300)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_serve_worker, args=(2, _free_port(), table, ys, ret), nprocs=2, join=True)
+    assert ret[1] == 2                                           # two generations served, then the stop signal
+    assert np.array_equal(ret[0][0], ref.astype(np.float32))
+    assert np.array_equal(ret[0][1], ref.astype(np.float32)[::-1])
