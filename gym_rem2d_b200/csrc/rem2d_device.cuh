@@ -410,8 +410,10 @@ public:
         setBi(BF_FLAGS, b, Bi(BF_FLAGS, b) | BFL_MOVED);
     }
     __device__ __forceinline__ bool overlap_edge(int e, int b) {
+        return overlap_edge_box(e, B(BF_FLX, b), B(BF_FLY, b), B(BF_FHX, b), B(BF_FHY, b));
+    }
+    __device__ __forceinline__ bool overlap_edge_box(int e, float blx, float bly, float bhx, float bhy) {
         float alx = __ldg(&ter->flx[e]), aly = __ldg(&ter->fly[e]), ahx = __ldg(&ter->fhx[e]), ahy = __ldg(&ter->fhy[e]);
-        float blx = B(BF_FLX, b), bly = B(BF_FLY, b), bhx = B(BF_FHX, b), bhy = B(BF_FHY, b);
         float d1x = blx - ahx, d1y = bly - ahy, d2x = alx - bhx, d2y = aly - bhy;
         if (d1x > 0.0f || d1y > 0.0f) return false;
         if (d2x > 0.0f || d2y > 0.0f) return false;
@@ -515,21 +517,28 @@ public:
         return -1;
     }
     // b2ContactManager::FindNewContacts: new pairs in ascending (edge, body) order, each becomes the newest
+    // The first pass asks, body by body over the body's own edge range, whether ANY new pair exists (almost never: a handful
+    // per episode); only then the pairs are enumerated in Box2D's order over the union of the ranges.
     __device__ void find_new_contacts() {
         int elo = ter->n_edges, ehi = -1;
-        int any = 0;
+        bool any = false, has = false;
+        int nc = Si(S_NC);
         for (int b = 0; b < nb; ++b) {
             if (!(Bi(BF_FLAGS, b) & BFL_MOVED)) continue;
-            any = 1;
-            double l = floor(((double)B(BF_FLX, b) - 0.25) / (double)ter->step) - 1.0;
-            double u = ceil(((double)B(BF_FHX, b) + 0.25) / (double)ter->step) + 1.0;
+            any = true;
+            const float blx = B(BF_FLX, b), bly = B(BF_FLY, b), bhx = B(BF_FHX, b), bhy = B(BF_FHY, b);
+            double l = floor(((double)blx - 0.25) / (double)ter->step) - 1.0;
+            double u = ceil(((double)bhx + 0.25) / (double)ter->step) + 1.0;
             int il = l < 0.0 ? 0 : (l > (double)(ter->n_edges - 1) ? ter->n_edges : (int)l);
             int iu = u < 0.0 ? -1 : (u > (double)(ter->n_edges - 1) ? ter->n_edges - 1 : (int)u);
             if (il < elo) elo = il;
             if (iu > ehi) ehi = iu;
+            if (!has)
+                for (int e = il; e <= iu; ++e)
+                    if (overlap_edge_box(e, blx, bly, bhx, bhy) && find_contact(nc, b, e) < 0) { has = true; break; }
         }
         if (!any) return;
-        int nc = Si(S_NC);
+        if (!has) { elo = 0; ehi = -1; }
         for (int e = elo; e <= ehi; ++e) {
             for (int b = 0; b < nb; ++b) {
                 if (!(Bi(BF_FLAGS, b) & BFL_MOVED)) continue;
@@ -565,8 +574,9 @@ public:
                 if (iu - il >= 24) special = true;            // (a proxy spanning > 24 edges: the leader scans it the slow way)
                 else {
                     int mask = 0;
+                    const float blx = B(BF_FLX, b), bly = B(BF_FLY, b), bhx = B(BF_FHX, b), bhy = B(BF_FHY, b);
                     for (int e = il; e <= iu; ++e)
-                        if (overlap_edge(e, b) && find_contact(nc0, b, e) < 0) mask |= 1 << (e - il);
+                        if (overlap_edge_box(e, blx, bly, bhx, bhy) && find_contact(nc0, b, e) < 0) mask |= 1 << (e - il);
                     if (mask) { w = il | (mask << 8); has = true; }
                 }
             }

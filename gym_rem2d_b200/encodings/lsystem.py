@@ -57,12 +57,17 @@ class Rule:
                 self.module.availableConnections.append(victim.parentConnectionSite)
                 self.module.children.remove(victim)
 
-    def update(self, index):
+    def update(self, index, share=False):
         """Fresh copies of this rule's products, numbered from index+1 (LSystem.py:114-124)."""
         out = []
         for c in self.module.children:
             index += 1
-            sym = copy.deepcopy(c)
+            if share:                       # field-by-field copy of a product symbol (ints, enum members, a list of enum members)
+                sym = C_Module.__new__(C_Module)
+                sym.__dict__.update(c.__dict__)
+                sym.availableConnections = list(c.availableConnections)
+            else:
+                sym = copy.deepcopy(c)
             sym.children = []
             sym.index = index
             sym.handled = False
@@ -81,45 +86,52 @@ class LSystem:
             self.maxModules = 20
         self.rules = [Rule(i, moduleList) for i in range(len(moduleList))]
 
-    def create(self, treedepth):
+    def create(self, treedepth, share=False):
+        """``share=True`` (used by the population flattener, which only READS the tree): the nodes reference the type's
+        module and controller instead of deep copies of them - the same tree, 4x cheaper to build. The default is the
+        reference's behaviour (every node owns its copies)."""
         # the argument is ignored; self.treeDepth is used (LSystem.py:157,165)
-        base = copy.deepcopy(self.rules[0].module)
+        if share:
+            base = C_Module.__new__(C_Module)
+            base.__dict__.update(self.rules[0].module.__dict__)
+        else:
+            base = copy.deepcopy(self.rules[0].module)
         base.children = []
         base.index = 0
         index = 0
         for _ in range(self.treeDepth):
-            index = self.iterate(base, index, 0)
+            index = self.iterate(base, index, 0, share)
         tree = _tree.Tree(self.moduleList)
-        self.recursiveNodeGen(-1, base, tree, 0)
+        self.recursiveNodeGen(-1, base, tree, 0, share)
         return tree
 
-    def iterate(self, currentSymbol, index, depth):
+    def iterate(self, currentSymbol, index, depth, share=False):
         if index > self.maxModules:
             return index
         if not currentSymbol.handled:
             currentSymbol.handled = True
             if len(currentSymbol.children) > 0:
                 raise Exception("if symbol was not handled it shouldn't contain children")
-            index, symbols = self.rules[currentSymbol.moduleRef].update(index)
+            index, symbols = self.rules[currentSymbol.moduleRef].update(index, share)
             for s in symbols:
                 s.parent = currentSymbol.index
                 currentSymbol.children.append(s)
         else:
             for c in currentSymbol.children:
-                index = self.iterate(c, index, depth + 1)
+                index = self.iterate(c, index, depth + 1, share)
         return index
 
-    def recursiveNodeGen(self, parentIndex, m, tree, nodeCounter):
+    def recursiveNodeGen(self, parentIndex, m, tree, nodeCounter, share=False):
         if nodeCounter > self.maxModules:
             return nodeCounter
         proto = self.moduleList[m.moduleRef]
         node = _tree.Node(m.index, parentIndex, m.moduleRef, m.parentConnectionSite,
-                          copy.deepcopy(proto.controller))
-        node.module_ = copy.deepcopy(proto)
+                          proto.controller if share else copy.deepcopy(proto.controller))
+        node.module_ = proto if share else copy.deepcopy(proto)
         tree.nodes.append(node)
         for c in m.children:
             nodeCounter += 1
-            nodeCounter = self.recursiveNodeGen(c.parent, c, tree, nodeCounter)
+            nodeCounter = self.recursiveNodeGen(c.parent, c, tree, nodeCounter, share)
         return nodeCounter
 
     def mutate(self, MORPH_MUTATIONRATE, MUTATION_RATE, MUT_SIGMA):

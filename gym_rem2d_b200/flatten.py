@@ -18,6 +18,7 @@ import numpy as np
 
 from . import constants as K
 from .modules import Circular2D
+from .encodings.lsystem import LSystem
 
 
 def _f32(v):
@@ -216,7 +217,8 @@ def flatten_population(individuals, tree_depth=None):
     for ind in individuals:
         if hasattr(ind, "genome"):
             depth = tree_depth if tree_depth is not None else ind.tree_depth
-            tree = ind.genome.create(depth)
+            # the flattener only reads the tree: the L-system may hand out nodes that share the type's module / controller
+            tree = ind.genome.create(depth, share=True) if isinstance(ind.genome, LSystem) else ind.genome.create(depth)
             tables.append(flatten_tree(tree, ind.genome.moduleList))
         else:
             tables.append(flatten_tree(ind))

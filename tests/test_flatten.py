@@ -109,3 +109,25 @@ def test_population_table_select_roundtrip():
         assert np.array_equal(getattr(sub, k), getattr(ref, k)), k
     joff = pop.joint_off()
     assert joff[-1] == pop.n_bodies - pop.n_creatures
+
+
+def test_lsystem_shared_expansion_gives_the_same_table():
+    """flatten_population expands L-systems without the per-node deep copies (it only reads the tree): the table must equal
+    the one built from the reference-style tree, for fresh and for mutated genomes."""
+    import random
+    from gym_rem2d_b200.ea import default_config
+    from gym_rem2d_b200.individual import Individual
+    from gym_rem2d_b200.modules import get_module_list
+    from gym_rem2d_b200.flatten import flatten_population, flatten_tree, pack
+    random.seed(11); np.random.seed(11)
+    cfg = default_config(enc="lsystem")
+    pop = [Individual.random(get_module_list(), cfg) for _ in range(120)]
+    for rnd in range(3):
+        fast = flatten_population(pop, 8)
+        slow = pack([flatten_tree(ind.genome.create(8), ind.genome.moduleList) for ind in pop])
+        for name in ("body_off", "shape", "hx", "hy", "x0", "y0", "a0", "node_index", "type_ref", "joint_parent", "anchor_a",
+                     "anchor_b", "lower", "upper", "max_torque", "ctrl"):
+            a, b = getattr(fast, name), getattr(slow, name)
+            assert a.dtype == b.dtype and a.shape == b.shape and a.tobytes() == b.tobytes(), name
+        for ind in pop:
+            Individual.mutate(0.3, 0.3, 0.3, ind)
