@@ -115,6 +115,7 @@ def ea_bench(args, rank, local_rank, world, cores):
         random.seed(args.seed)
         np.random.seed(args.seed)
         run = ea.run2D(cfg, "", workers=max(2, cores - 2), distributed=world > 1)     # pool first: before CUDA exists here
+        run.materialize_result = False           # the final population stays packed (nothing reads it here)
     import torch
     import torch.distributed as dist
     if world > 1:

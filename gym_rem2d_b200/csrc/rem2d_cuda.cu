@@ -162,6 +162,7 @@ struct Options {
     int warp_mode_max = -1;      // largest population that runs one warp per creature from tick 0 (-1: 48 per SM)
     int park_ticks = -1;         // park threshold of the queue mode (-1: automatic, 0: never park)
     double park_cap = -1.0;      // fraction of a class that may be parked (-1: automatic)
+    int image = -1;              // kernel image of the episode launches (-1: automatic, 0: ~200 registers, 1: 128 registers)
     int park_late_ticks = -1;    // park threshold of creatures pulled after the first round (-1: same as park_ticks)
     int park_lead = 0;           // park a creature as soon as its root is where the wall of death will be at the park threshold.
                                  // Measured and rejected as default: more creatures are parked, and early, while the GPU is still full -
@@ -259,13 +260,14 @@ static bool set_option(Options& o, const char* name, double v) {
     else if (n == "second_group_shift") o.second_group_shift = std::max(-1, std::min(5, (int)v));
     else if (n == "trace") o.trace = (int)v;
     else if (n == "phased") o.phased = (int)v;
+    else if (n == "image") o.image = std::max(-1, std::min(1, (int)v));
     else if (n.rfind("class_gs_", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] < '0' + N_CLASSES) o.class_gs[n[9] - '0'] = (int)v;
     else return false;
     return true;
 }
 static void options_from_env(Options& o) {
     static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "park_late_ticks", "park_lead", "smem_budget_kb", "small_weight", "min_class",
-                                  "group_shift", "tail_group_shift", "second_group_shift", "trace"};
+                                  "group_shift", "tail_group_shift", "second_group_shift", "trace", "image"};
     for (const char* n : names) {
         std::string env = "REM2D_";
         for (const char* q = n; *q; ++q) env += (char)toupper(*q);
@@ -508,7 +510,18 @@ static void choose_groups_and_grids(rem2d_handle* h) {
     // under-filled GPU <=> everything fits with one lane per creature in the 128-register image: then widen (below)
     h->image = 1;
     bool all_fit = size_grids(h);
-    if (!all_fit) { h->image = 0; size_grids(h); }
+    if (!all_fit) {
+        // Throughput-bound: one lane per creature - except the largest class (33-44 bodies): its 4.6 KB of solver state per
+        // creature make a 32-creature CTA 148 KB of shared memory, ONE resident warp per SM at a 5 ms tick. 8 lanes per creature
+        // (4 creatures, 19 KB per CTA) pack the same residency into warps that tick twice as fast and fit beside the other
+        // classes' CTAs. Measured on EA-configured populations (max_size 40; tools/ea_pop_sweep.py, profiles/r2_ea_pop_sweep.txt):
+        // 1.5-1.6x on the whole evaluation (1946 -> 1271 ms, 3311 -> 2112, 5925 -> 3676); widening the 23-32 body class as well
+        // gains nothing, the smaller classes lose (the bench population, <= 21 bodies, is unaffected).
+        for (int k = 0; k < N_CLASSES; ++k)
+            if (!forced[k]) h->cur_gs[k] = g_classes(k).nb > 32 ? 3 : 0;
+        h->image = h->opt.image >= 0 ? h->opt.image : 0;
+        size_grids(h);
+    }
     for (int k = 0; k < N_CLASSES; ++k) { h->cls[k].grid2 = 0; h->cls[k].gs2 = 0; }
     if (!all_fit) {
         // Throughput-bound population: one lane per creature, lanes refilled from the class queue. OPTION "second_group_shift"

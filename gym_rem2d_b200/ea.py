@@ -85,6 +85,47 @@ def _random_chunk(args):
     return [Individual.random(module_list, config) for _ in range(n)]
 
 
+class PackedIndividual:
+    """An individual kept as its pickle. Between two generations the driving process needs of an individual only its fitness
+    (tournaments) and its lifetime (scheduling hint); the object itself is needed by the WORKER that varies it. Shipping objects
+    costs the driving process a serial pickle.dumps per parent and a serial pickle.loads per offspring - measured 0.17 + 0.15 ms
+    per individual, 7-19 s per generation at population 65536, more than everything else together - while bytes go through
+    the pipe as one copy. ``unpack()`` gives the Individual (checkpoints, the elite, the result of the run)."""
+    __slots__ = ("blob", "fitness", "lifetime")
+
+    def __init__(self, blob, fitness=0.0, lifetime=0):
+        self.blob, self.fitness, self.lifetime = blob, fitness, lifetime
+
+    @classmethod
+    def pack(cls, ind):
+        return cls(pickle.dumps(ind, pickle.HIGHEST_PROTOCOL), getattr(ind, "fitness", 0.0), getattr(ind, "lifetime", 0))
+
+    def unpack(self):
+        ind = pickle.loads(self.blob)
+        ind.fitness, ind.lifetime = self.fitness, self.lifetime
+        return ind
+
+
+def _random_chunk_packed(args):
+    """Worker: ``n`` random individuals, returned as pickles + their flattened table."""
+    inds = _random_chunk(args[:4])
+    return [pickle.dumps(o, pickle.HIGHEST_PROTOCOL) for o in inds], flatten_population(inds, args[4])
+
+
+def _vary_chunk_packed(args):
+    """Worker: like _vary_chunk on pickles. ``blobs`` holds every distinct parent of the chunk once, ``idx`` the chunk's
+    parents as indices into it; every occurrence is unpickled separately (= ``toolbox.clone``)."""
+    blobs, idx, depth, mmr, mr, sigma, seed = args
+    random.seed(seed)
+    np.random.seed(seed % (2 ** 32))
+    parents = [pickle.loads(blobs[i]) for i in idx]
+    for o in parents:
+        Individual.mutate(mmr, mr, sigma, o)
+        o.fitness = 0
+    table = flatten_population(parents, depth)
+    return [pickle.dumps(o, pickle.HIGHEST_PROTOCOL) for o in parents], table
+
+
 def _vary_chunk(args):
     """Worker: variation + expansion of one chunk of selected parents (REM2D_main.py:283-290 + evaluate's genome.create).
     Parents arrive pickled (= the deep copy of ``toolbox.clone``); every chunk is seeded so that a run is reproducible
@@ -92,6 +133,11 @@ def _vary_chunk(args):
     parents, depth, mmr, mr, sigma, seed = args
     random.seed(seed)
     np.random.seed(seed % (2 ** 32))
+    seen = set()
+    for k, o in enumerate(parents):          # a parent that won several tournaments arrives as ONE object: clone the repeats
+        if id(o) in seen:
+            parents[k] = copy.deepcopy(o)
+        seen.add(id(o))
     for o in parents:
         Individual.mutate(mmr, mr, sigma, o)
         o.fitness = 0
@@ -122,11 +168,13 @@ class run2D:
         self.generation_offset = 0           # generations already done by the run this one resumes
         self.expected_ticks = None           # scheduling hint for the next evaluation (parents' lifetimes)
         self.last_lifetimes = None
+        self.last_device_s = 0.0
         # evaluate as soon as this many expanded creatures have arrived (0: expand everything, then evaluate once). Off by
         # default: measured at population 65536 with 14 workers on a 16-core box, the evaluation's host thread (it polls the park
         # counters and launches the tail kernels) is starved by the busy workers and the chunked evaluations take 6-8 s per
         # generation instead of 1 s for one evaluation of the whole table (profiles/r2_ea_config5.json)
         self.pipeline_creatures = 0
+        self.materialize_result = True       # run_deap returns Individuals (False: PackedIndividuals where the population was packed)
         # persistent workers, started BEFORE any CUDA work of this process (the engine is created lazily, later)
         # (forkserver re-imports __main__ in the workers, which an interactive / stdin main cannot offer: plain fork there - still
         # before any CUDA work of this process)
@@ -171,6 +219,8 @@ class run2D:
             env.engine.set_priority(self.expected_ticks)        # offspring are expected to live about as long as their parents
         fit = env.evaluate(table=table, steps=self.EVALUATION_STEPS)
         self.last_lifetimes = np.asarray(env.last_ticks)
+        if hasattr(env, "engine"):
+            self.last_device_s = env.engine.last_step_ms() * 1e-3      # the episode launches alone (CUDA events)
         return [float(f) for f in fit], int(env.last_ticks.sum())
 
     def evaluate_batch(self, individuals):
@@ -191,12 +241,14 @@ class run2D:
         arrived they are evaluated on the GPU while the workers continue - evaluation hides behind the host-side expansion,
         which dominates a generation at large population sizes. Returns (offspring, fitness list, timing)."""
         t0 = time.perf_counter()
-        if self.pool is None or len(parents) < 4 * self.workers or self.distributed or self.pipeline_creatures <= 0:
+        packed = bool(parents) and isinstance(parents[0], PackedIndividual)
+        if self.pool is None or len(parents) < 4 * self.workers or self.distributed or self.pipeline_creatures <= 0 or packed:
             offspring, table = self.vary_and_expand(parents)
             t1 = time.perf_counter()
             fit, steps = self.evaluate_table(table)
             t2 = time.perf_counter()
-            return offspring, fit, {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "evaluate_hidden_s": 0.0, "creature_steps": steps}
+            return offspring, fit, {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "evaluate_hidden_s": 0.0, "creature_steps": steps,
+                                    "evaluate_device_s": self.last_device_s, "mean_bodies": float(np.diff(table.body_off).mean())}
         jobs = [(c, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, random.getrandbits(48))
                 for c in self._chunks(parents)]
         offspring, fit, pending, n_pending, steps, eval_s = [], [], [], 0, 0, 0.0
@@ -216,6 +268,20 @@ class run2D:
 
     def vary_and_expand(self, parents):
         """clone + mutate + expand: in the workers when there is a pool, else here."""
+        if self.pool is not None and parents and isinstance(parents[0], PackedIndividual):
+            jobs = []
+            for chunk in self._chunks(parents):
+                slot, blobs, idx = {}, [], []
+                for p in chunk:
+                    k = slot.get(id(p))
+                    if k is None:
+                        k = slot[id(p)] = len(blobs)
+                        blobs.append(p.blob)
+                    idx.append(k)
+                jobs.append((blobs, idx, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA,
+                             random.getrandbits(48)))
+            parts = self.pool.map(_vary_chunk_packed, jobs)
+            return [PackedIndividual(b) for bl, _ in parts for b in bl], concat([t for _, t in parts])
         if self.pool is not None and len(parents) >= 4 * self.workers:
             jobs = [(c, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, random.getrandbits(48))
                     for c in self._chunks(parents)]
@@ -242,10 +308,14 @@ class run2D:
                 setattr(self.fitnessData, k, list(getattr(self.fitnessData, k))[:self.generation_offset])
         return self.run_deap(config or self.config, population=population, n_generations=n_generations)
 
+    @staticmethod
+    def _unpacked(population):
+        return [p.unpack() if isinstance(p, PackedIndividual) else p for p in population]
+
     def _checkpoint(self, population, g):
         from . import refpickle
         refpickle.dump(self.fitnessData, self.SAVE_FILE_DIRECTORY)
-        refpickle.dump(population, self.SAVE_FILE_DIRECTORY + self.POPULATION_FILE + str(g))
+        refpickle.dump(self._unpacked(population), self.SAVE_FILE_DIRECTORY + self.POPULATION_FILE + str(g))
 
     def run_deap(self, config, population=None, useTQDM=False, n_generations=None):
         from . import refpickle
@@ -254,15 +324,24 @@ class run2D:
         if n_generations is not None:
             N_GENERATIONS = n_generations
         rank0 = (not self.distributed) or int(os.environ.get("RANK", "0")) == 0
+        # large populations with a worker pool: the population lives here as pickles (see PackedIndividual)
+        packed = self.pool is not None and self.POPULATION_SIZE >= 64 * self.workers
         if population is None:
-            if self.pool is not None and self.POPULATION_SIZE >= 64 * self.workers:
+            if packed:
                 sizes = [len(c) for c in self._chunks(list(range(self.POPULATION_SIZE)))]
-                parts = self.pool.map(_random_chunk, [(n, self.moduleList, self.config, random.getrandbits(48)) for n in sizes])
-                population = [ind for part in parts for ind in part]
+                parts = self.pool.map(_random_chunk_packed, [(n, self.moduleList, self.config, random.getrandbits(48), self.TREE_DEPTH)
+                                                             for n in sizes])
+                population = [PackedIndividual(b) for bl, _ in parts for b in bl]
+                fitness_values, _ = self.evaluate_table(concat([t for _, t in parts]))
             else:
                 population = [Individual.random(self.moduleList, self.config) for _ in range(self.POPULATION_SIZE)]
-            for ind, fit in zip(population, self.evaluate_batch(population)):
+                fitness_values = self.evaluate_batch(population)
+            for k, (ind, fit) in enumerate(zip(population, fitness_values)):
                 ind.fitness = fit
+                if self.last_lifetimes is not None and len(self.last_lifetimes) == len(population):
+                    ind.lifetime = int(self.last_lifetimes[k])
+        elif packed:
+            population = [p if isinstance(p, PackedIndividual) else PackedIndividual.pack(p) for p in population]
         for i in range(N_GENERATIONS):
             g = self.generation_offset + i                     # absolute generation index (file suffix)
             t0 = time.perf_counter()
@@ -286,8 +365,10 @@ class run2D:
                     if o.fitness > bestfit:
                         bestfit, best = o.fitness, o
                 if best is not None:
-                    refpickle.dump(best, self.SAVE_FILE_DIRECTORY + self.BEST_INDIVIDUAL_FILE + str(g))
+                    refpickle.dump(self._unpacked([best])[0], self.SAVE_FILE_DIRECTORY + self.BEST_INDIVIDUAL_FILE + str(g))
             if time.time() - self.start_time > int(config.get("ea", "wallclock_time_limit", fallback=str(2 ** 62))):
                 break
+        if self.materialize_result:
+            population = self._unpacked(population)
         self.population = population
         return population

@@ -12,6 +12,7 @@ level of the tree. ``_f32`` marks exactly those round trips (SURVEY.md Appendix 
 the emitted table bit-exact against the reference (tests/test_flatten.py, golden fixtures).
 """
 import math
+import struct
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -21,8 +22,18 @@ from .modules import Circular2D
 from .encodings.lsystem import LSystem
 
 
+_F32 = struct.Struct("f")
+
+
 def _f32(v):
-    return float(np.float32(v))
+    """``v`` rounded to float32 (C cast, round-to-nearest-even - what pybox2d's float members do), as a Python float."""
+    try:
+        return _F32.unpack(_F32.pack(v))[0]
+    except OverflowError:                    # beyond the float32 range: inf, like the cast
+        return float(np.float32(v))
+
+
+_JOINT_LOWER32, _JOINT_UPPER32 = _f32(K.JOINT_LOWER), _f32(K.JOINT_UPPER)
 
 
 @dataclass
@@ -61,7 +72,7 @@ def flatten_tree(tree, module_list=None, terrain_height=K.TERRAIN_HEIGHT):
         module_list = tree.moduleList
     out = CreatureTable()
     slot_of = {}          # id(node) -> body slot, for nodes that produced a body
-    handled = []          # nodes that went through create_component (built OR dropped), in order
+    handled = {}          # node index -> FIRST node with that index that went through create_component (built OR dropped)
     out.expressed = [-1] * len(nodes)
 
     def emit(pos_of_node, node, x, y, angle, mod):
@@ -92,18 +103,14 @@ def flatten_tree(tree, module_list=None, terrain_height=K.TERRAIN_HEIGHT):
             mod = _module_of(node, module_list)
             if not mod.too_low(K.ROOT_Y, terrain_height):
                 emit(k, node, K.ROOT_X, K.ROOT_Y, 0.0, mod)
-            handled.append(node)
+            handled.setdefault(node.index, node)
             done.add(k)
 
     # pass 2: every other node, in list order, if its parent produced a body
     for k, node in enumerate(nodes):
         if k in done:
             continue
-        parent = None
-        for h in handled:                       # get_component_index: first handled node with that index
-            if h.index == node.parent:
-                parent = h
-                break
+        parent = handled.get(node.parent)       # get_component_index: first handled node with that index
         if parent is None or id(parent) not in slot_of:
             continue                             # parent missing or dropped: node is never expressed
         ps = slot_of[id(parent)]
@@ -121,7 +128,7 @@ def flatten_tree(tree, module_list=None, terrain_height=K.TERRAIN_HEIGHT):
             site, s_ang = pmod.connection_site(con, px, py, pa)
         mod = _module_of(node, module_list)
         cx, cy = mod.child_placement(site, s_ang)
-        handled.append(node)
+        handled.setdefault(node.index, node)
         if mod.too_low(cy, terrain_height):
             continue                             # dropped (simple_module.py:268-271, circular_module.py:186-189)
         slot = emit(k, node, cx, cy, 0 + s_ang, mod)
@@ -134,8 +141,8 @@ def flatten_tree(tree, module_list=None, terrain_height=K.TERRAIN_HEIGHT):
         out.joint_parent.append(ps)
         out.anchor_a.append((_f32(math.cos(ang_a) * dis_a), _f32(math.sin(ang_a) * dis_a)))
         out.anchor_b.append((_f32(math.cos(ang_b) * dis_b), _f32(math.sin(ang_b) * dis_b)))
-        out.lower.append(_f32(K.JOINT_LOWER))
-        out.upper.append(_f32(K.JOINT_UPPER))
+        out.lower.append(_JOINT_LOWER32)
+        out.upper.append(_JOINT_UPPER32)
         out.max_torque.append(_f32(mod.torque))
     return out
 

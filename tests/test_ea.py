@@ -83,6 +83,49 @@ def test_parallel_expansion_equals_serial():
     b.close()
 
 
+def test_packed_population_generations(tmp_path):
+    """Large populations with a worker pool live in the driving process as pickles (PackedIndividual): same loop, same
+    files, Individuals come back at the end; a parent that wins several tournaments yields INDEPENDENT offspring."""
+    random.seed(6)
+    cfg = ea.default_config(directory=str(tmp_path), enc="lsystem", mr=0.3, mmr=0.3, ms=0.3)
+    cfg["ea"]["batch_size"] = "160"
+    cfg["experiment"]["checkpoint_frequency"] = "2"
+    run = ea.run2D(cfg, str(tmp_path), env=StubEnv(), workers=2)
+    try:
+        pop = run.run_deap(cfg, n_generations=3)
+        assert len(pop) == 160 and all(isinstance(p, Individual) for p in pop)
+        assert len({id(p) for p in pop}) == 160
+        from gym_rem2d_b200.flatten import flatten_population
+        nb = np.diff(flatten_population(pop, run.TREE_DEPTH).body_off)
+        assert [p.fitness for p in pop] == [float(n) for n in nb]            # fitness travelled with the right individual
+        assert [p.lifetime for p in pop] == [int(n) * 10 for n in nb]
+        from gym_rem2d_b200 import refpickle
+        saved = refpickle.load(tmp_path / "s_pop2")
+        assert len(saved) == 160 and isinstance(saved[0], Individual)
+        assert any(f.startswith("s_elite") for f in os.listdir(tmp_path))
+        # one parent, many tournaments won: every offspring is its own clone with its own mutations
+        one = ea.PackedIndividual.pack(pop[0])
+        random.seed(9)
+        off, table = run.vary_and_expand([one] * 160)
+        assert table.n_creatures == 160 and len({o.blob for o in off}) > 100
+        # a resumed run packs the loaded population again
+        run2 = ea.run2D(cfg, str(tmp_path), env=StubEnv(), workers=2)
+        run2.materialize_result = False
+        pop2 = run2.run(cfg, continue_progression=True, n_generations=1)
+        assert len(pop2) == 160 and isinstance(pop2[0], ea.PackedIndividual) and isinstance(pop2[0].unpack(), Individual)
+        run2.close()
+    finally:
+        run.close()
+
+
+def test_repeated_parents_are_cloned_in_the_worker():
+    random.seed(8)
+    cfg = ea.default_config(enc="lsystem")
+    a = Individual.random(config=cfg)
+    off, table = ea._vary_chunk(pickle.loads(pickle.dumps(([a, a, a], 8, 0.5, 0.5, 0.5, 123))))
+    assert len({id(o) for o in off}) == 3 and table.n_creatures == 3
+
+
 @pytest.mark.gpu
 def test_generations_on_the_gpu():
     random.seed(4)
