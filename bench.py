@@ -126,7 +126,7 @@ def ea_bench(args, rank, local_rank, world, cores):
         from gym_rem2d_b200.env import BatchedModular2D
         env = BatchedModular2D(device=local_rank)
         env.seed(K.TERRAIN_SEED)
-        rdist.serve_evaluations(env.engine, K.EVALUATION_STEPS)
+        rdist.serve_evaluations(env.engine, K.EVALUATION_STEPS, gather_ticks=True)
         dist.destroy_process_group()
         return
     t0 = time.perf_counter()
@@ -138,7 +138,7 @@ def ea_bench(args, rank, local_rank, world, cores):
     gens = run.generation_log
     steps = sum(g["creature_steps"] for g in gens)
     secs = sum(g["seconds"] for g in gens)
-    print(json.dumps({"metric": "creature-steps/sec (EA loop, config 5)", "value": steps * (world if world > 1 else 1) / secs if world == 1 else None,
+    print(json.dumps({"metric": "creature-steps/sec (EA loop, config 5)", "value": steps / secs,
                       "unit": "creature-steps/s", "n_gpus": world, "population": args.pop, "generations": len(gens), "host_workers": max(2, cores - 2),
                       "seconds_per_generation": secs / max(1, len(gens)),
                       "per_generation": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in g.items()} for g in gens],

@@ -50,12 +50,13 @@ def gather_fitness(local_fitness, local_idx, n_total, device=None):
     return out
 
 
-def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=None):
+def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=None, gather_ticks=False):
     """Evaluate this rank's shard of ``table`` on ``engine`` and gather everyone's fitness: the multi-GPU form of
     ``pool.map(evaluate, population, chunksize=ceil(pop/n))`` (REM2D_main.py:256-262). ``engine`` is a long-lived
     ``capi.Engine`` (its device buffers are grow-only and reused from generation to generation); a zero-argument factory is
     accepted for one-off calls. Returns (fitness of the WHOLE population in population order, float32; this rank's
-    creature-steps)."""
+    creature-steps). With ``gather_ticks`` the lifetimes are gathered as well (one more all_gather) and the second value is the
+    lifetime of every creature of the whole population (int32) - every rank must pass the same flag."""
     import torch.distributed as dist
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -63,6 +64,9 @@ def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=Non
     sub, idx = shard_population(table, rank, world)
     eng = engine() if callable(engine) else engine
     fit, ticks = eng.evaluate(sub, max_ticks)
+    if gather_ticks:                       # lifetimes <= max_ticks are exact in float32
+        return (gather_fitness(fit, idx, table.n_creatures, device=device),
+                gather_fitness(ticks, idx, table.n_creatures, device=device).astype(np.int32))
     return gather_fitness(fit, idx, table.n_creatures, device=device), int(ticks.sum())
 
 
@@ -110,21 +114,22 @@ _DTYPES = (np.int32, np.uint8, np.float32, np.float32, np.float32, np.float32, n
            np.float32, np.float32, np.float32, np.float32, np.float64)
 
 
-def evaluate_broadcast(table, engine, max_ticks, device=None):
+def evaluate_broadcast(table, engine, max_ticks, device=None, gather_ticks=False):
     """Collective: rank 0 passes the generation's table (None = stop), the others pass None; everybody returns the fitness of
-    the whole population (or None on stop)."""
+    the whole population (or None on stop) and what evaluate_sharded returns second."""
     import torch.distributed as dist
     table = broadcast_table(table, 0, device)
     if table is None:
         return None, 0
-    return evaluate_sharded(table, engine, max_ticks, dist.get_rank(), dist.get_world_size(), device)
+    return evaluate_sharded(table, engine, max_ticks, dist.get_rank(), dist.get_world_size(), device, gather_ticks)
 
 
-def serve_evaluations(engine, max_ticks, device=None):
-    """Body of every rank != 0 while rank 0 runs the evolutionary loop: evaluate shards until rank 0 sends the stop signal."""
+def serve_evaluations(engine, max_ticks, device=None, gather_ticks=False):
+    """Body of every rank != 0 while rank 0 runs the evolutionary loop: evaluate shards until rank 0 sends the stop signal.
+    ``gather_ticks`` as rank 0 passes it (ea.run2D: True)."""
     n = 0
     while True:
-        fit, _ = evaluate_broadcast(None, engine, max_ticks, device)
+        fit, _ = evaluate_broadcast(None, engine, max_ticks, device, gather_ticks)
         if fit is None:
             return n
         n += 1

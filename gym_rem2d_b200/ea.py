@@ -213,8 +213,9 @@ class run2D:
         if self.distributed:
             # rank 0 drives the loop and broadcasts the generation's table; the other ranks sit in distributed.serve_evaluations
             from . import distributed as rdist
-            fit, steps = rdist.evaluate_broadcast(table, env.engine, self.EVALUATION_STEPS)
-            return [float(f) for f in fit], steps
+            fit, lifetimes = rdist.evaluate_broadcast(table, env.engine, self.EVALUATION_STEPS, gather_ticks=True)
+            self.last_lifetimes = lifetimes
+            return [float(f) for f in fit], int(lifetimes.sum())
         if self.expected_ticks is not None and len(self.expected_ticks) == table.n_creatures and hasattr(env, "engine"):
             env.engine.set_priority(self.expected_ticks)        # offspring are expected to live about as long as their parents
         fit = env.evaluate(table=table, steps=self.EVALUATION_STEPS)

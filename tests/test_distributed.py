@@ -83,12 +83,12 @@ def _serve_worker(rank, world, port, table, ys, ret):
         out = []
         for gen in range(2):
             sub = table if gen == 0 else table.select(np.arange(table.n_creatures)[::-1].copy())
-            fit, steps = rdist.evaluate_broadcast(sub, e, 300)
-            out.append(fit)
+            fit, lifetimes = rdist.evaluate_broadcast(sub, e, 300, gather_ticks=True)
+            out.append((fit, lifetimes))
         assert rdist.broadcast_table(None, 0) is None          # stop signal
         ret[0] = out
     else:
-        ret[rank] = rdist.serve_evaluations(e, 300)
+        ret[rank] = rdist.serve_evaluations(e, 300, gather_ticks=True)
     dist.destroy_process_group()
 
 
@@ -99,10 +99,11 @@ def test_rank0_drives_and_the_other_ranks_serve():
     from oracle.oracle import OracleEngine
     e = OracleEngine()
     e.set_terrain(ys, K.TERRAIN_STEP)
-    ref, _ = e.evaluate(table, 300)
+    ref, ref_ticks = e.evaluate(table, 300)
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_serve_worker, args=(2, _free_port(), table, ys, ret), nprocs=2, join=True)
     assert ret[1] == 2                                           # two generations served, then the stop signal
-    assert np.array_equal(ret[0][0], ref.astype(np.float32))
-    assert np.array_equal(ret[0][1], ref.astype(np.float32)[::-1])
+    assert np.array_equal(ret[0][0][0], ref.astype(np.float32))
+    assert np.array_equal(ret[0][1][0], ref.astype(np.float32)[::-1])
+    assert np.array_equal(ret[0][0][1], ref_ticks) and np.array_equal(ret[0][1][1], ref_ticks[::-1])     # gathered lifetimes
