@@ -162,12 +162,14 @@ struct Options {
     int warp_mode_max = -1;      // largest population that runs one warp per creature from tick 0 (-1: 48 per SM)
     int park_ticks = -1;         // park threshold of the queue mode (-1: automatic, 0: never park)
     double park_cap = -1.0;      // fraction of a class that may be parked (-1: automatic)
+    int overflow_wave = 1;       // queue the CTAs a class could not seat in its first wave behind the first launches (see choose_groups_and_grids)
     int image = -1;              // kernel image of the episode launches (-1: automatic, 0: ~200 registers, 1: 128 registers)
     int park_late_ticks = -1;    // park threshold of creatures pulled after the first round (-1: same as park_ticks)
     int park_lead = 0;           // park a creature as soon as its root is where the wall of death will be at the park threshold.
                                  // Measured and rejected as default: more creatures are parked, and early, while the GPU is still full -
                                  // the tail launches wait 100-300 ms for resources (950-1200 ms against 800 ms)
     double smem_budget_kb = 227.0, small_weight = 1.0;
+    double wide_weight = 1.0;    // weight of the wide class next to one-lane classes in a throughput-bound mix (first wave)
     int min_class = 0;
     int group_shift = -1;        // log2 lanes per creature in the queue / step kernels (-1: per class default)
     int class_gs[N_CLASSES] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};   // per capacity class ("class_gs_<k>", -1: default)
@@ -200,6 +202,9 @@ struct rem2d_handle {
     bool results_valid = false;         // d_fitness/d_ticks/... were written by the episode kernel
     int n_sms = 0;
     int max_warps_per_sm[2] = {8, 16};  // resident warps of the two episode kernel images per SM by registers (occupancy API)
+    double first_wave_frac = 1.0;       // share of the shared memory the first-wave grids are sized for
+    int prio_high = 0;                  // greatest stream priority of the device (tail pool)
+    bool overflow_wave = false;         // the second launches are overflow waves of the first (same width, both refill)
     int image = 0;                      // kernel image of the current population (0: 200 registers, 1: 128 registers)
     int n_edges = 0;
     // population
@@ -254,6 +259,7 @@ static bool set_option(Options& o, const char* name, double v) {
     else if (n == "park_lead") o.park_lead = (int)v;
     else if (n == "smem_budget_kb") o.smem_budget_kb = v;
     else if (n == "small_weight") o.small_weight = v;
+    else if (n == "wide_weight") o.wide_weight = v;
     else if (n == "min_class") o.min_class = std::max(0, std::min(N_CLASSES - 1, (int)v));
     else if (n == "group_shift") o.group_shift = (int)v;
     else if (n == "tail_group_shift") o.tail_group_shift = std::max(0, std::min(5, (int)v));
@@ -261,13 +267,14 @@ static bool set_option(Options& o, const char* name, double v) {
     else if (n == "trace") o.trace = (int)v;
     else if (n == "phased") o.phased = (int)v;
     else if (n == "image") o.image = std::max(-1, std::min(1, (int)v));
+    else if (n == "overflow_wave") o.overflow_wave = (int)v != 0;
     else if (n.rfind("class_gs_", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] < '0' + N_CLASSES) o.class_gs[n[9] - '0'] = (int)v;
     else return false;
     return true;
 }
 static void options_from_env(Options& o) {
     static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "park_late_ticks", "park_lead", "smem_budget_kb", "small_weight", "min_class",
-                                  "group_shift", "tail_group_shift", "second_group_shift", "trace", "image"};
+                                  "group_shift", "tail_group_shift", "second_group_shift", "trace", "image", "overflow_wave", "wide_weight"};
     for (const char* n : names) {
         std::string env = "REM2D_";
         for (const char* q = n; *q; ++q) env += (char)toupper(*q);
@@ -353,10 +360,16 @@ int rem2d_create(const rem2d_config* cfg, rem2d_handle** out) {
         if ((e = cudaEventCreate(&c.t_begin)) != cudaSuccess || (e = cudaEventCreate(&c.t_end)) != cudaSuccess) return fail("cudaEventCreate", e);
     }
     if ((e = cudaEventCreate(&h->ev_start)) != cudaSuccess || (e = cudaEventCreate(&h->ev_stop)) != cudaSuccess) return fail("cudaEventCreate", e);
+    {   // tail launches and the polling copies run at the device's greatest stream priority: their CTAs / copies go ahead of
+        // the queued overflow-wave CTAs of the episode launches
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) h->prio_high = greatest;
+        else cudaGetLastError();
+    }
     h->tail_pool.assign(64, nullptr);
     for (auto& st : h->tail_pool)
-        if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate (tail pool)", e);
-    if ((e = cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate (poll)", e);
+        if ((e = cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, h->prio_high)) != cudaSuccess) return fail("cudaStreamCreate (tail pool)", e);
+    if ((e = cudaStreamCreateWithPriority(&h->poll_stream, cudaStreamNonBlocking, h->prio_high)) != cudaSuccess) return fail("cudaStreamCreate (poll)", e);
     if ((e = cudaEventCreateWithFlags(&h->pool_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaMallocHost(&h->h_poll, sizeof(int) * 16)) != cudaSuccess) return fail("cudaMallocHost", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -445,7 +458,7 @@ static int launch_reset(rem2d_handle* h);
 // run after it. Returns true iff EVERY creature of every class has a group from the start (one round, under-filled GPU).
 static bool size_grids(rem2d_handle* h, double warp_frac = 0.97) {
     const double smem_kb = h->opt.smem_budget_kb, small_weight = h->opt.small_weight;
-    double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98;
+    double budget = (double)h->n_sms * smem_kb * 1024.0 * 0.98 * h->first_wave_frac;
     double work[N_CLASSES], smem[N_CLASSES];
     bool fixed[N_CLASSES];
     for (int k = 0; k < N_CLASSES; ++k) {
@@ -456,6 +469,7 @@ static bool size_grids(rem2d_handle* h, double warp_frac = 0.97) {
         // p(G) times faster (measured tick latencies, profiles/r2_timeline_*.txt)
         static const double speedup[6] = {1.0, 1.15, 1.5, 1.9, 2.2, 2.5};
         work[k] *= (double)(1 << gs) / speedup[gs];
+        if (gs > 0 && h->first_wave_frac < 1.0) work[k] *= h->opt.wide_weight;
         h->cls[k].episode_grid = 0;
     }
     // warps_k = W * work_k with W such that sum_k warps_k * smem_k = budget: every class then needs about the same
@@ -509,6 +523,7 @@ static void choose_groups_and_grids(rem2d_handle* h) {
     }
     // under-filled GPU <=> everything fits with one lane per creature in the 128-register image: then widen (below)
     h->image = 1;
+    h->first_wave_frac = 1.0;
     bool all_fit = size_grids(h);
     if (!all_fit) {
         // Throughput-bound: one lane per creature - except the largest class (33-44 bodies): its 4.6 KB of solver state per
@@ -521,8 +536,21 @@ static void choose_groups_and_grids(rem2d_handle* h) {
             if (!forced[k]) h->cur_gs[k] = g_classes(k).nb > 32 ? 3 : 0;
         h->image = h->opt.image >= 0 ? h->opt.image : 0;
         size_grids(h);
+        // Mixed widths: the cost model's tick latencies are those of one-lane warps on moderately loaded SMs; next to
+        // hundreds of 8-lane warps the one-lane classes tick 2x slower than modelled (4.8 ms against 1.55 ms for the wide
+        // class) and a first wave that asks for all of the shared memory does not even fit (736 of 822 CTAs resident,
+        // the launches behind them held back). With an overflow wave it is better to seat 75 % statically and let the
+        // queued CTAs take the rest as it frees up: 3560 -> 2610 ms, 1930 -> 1600, 1155 -> 1130 ms on the three
+        // EA-configured populations; all-one-lane populations (the bench) lose 4 % with it and keep the full first wave.
+        bool mixed = false;
+        for (int k = 0; k < N_CLASSES; ++k) mixed |= h->cls[k].n_members > 0 && h->cur_gs[k] > 0;
+        if (mixed && h->opt.overflow_wave && h->opt.second_group_shift < 0 && h->opt.smem_budget_kb > 226.0) {
+            h->first_wave_frac = 0.75;
+            size_grids(h);
+        }
     }
     for (int k = 0; k < N_CLASSES; ++k) { h->cls[k].grid2 = 0; h->cls[k].gs2 = 0; }
+    h->overflow_wave = false;
     if (!all_fit) {
         // Throughput-bound population: one lane per creature, lanes refilled from the class queue. OPTION "second_group_shift"
         // (off by default): the creatures of the large classes that do not get a lane in the first round are run by a second
@@ -538,6 +566,23 @@ static void choose_groups_and_grids(rem2d_handle* h) {
             if (left <= 0 || g_classes(k).nb < 12 || forced[k]) continue;
             cs.gs2 = std::max(gs2, h->cur_gs[k]);
             cs.grid2 = (left + (32 >> cs.gs2) - 1) / (32 >> cs.gs2);
+        }
+        // OVERFLOW WAVE (default): the first-wave grids above come from a static cost model; when it is off for a population -
+        // measured on an EA-configured one: the 33-44 body class done after 1.9 s, the others at 3.1-3.6 s, with the freed 18 MB
+        // of shared memory idle in between (profiles/r2_timeline_ea_gen2_before.txt) - nothing could use the resources of a
+        // class that has finished. So every class also queues, BEHIND all first launches, the CTAs it could not seat: the
+        // work distributor places them as earlier CTAs exit, they pull from the same class queue, and a CTA that finds its
+        // queue empty exits at once. The hardware does the balancing.
+        if (gs2 < 0 && h->opt.overflow_wave) {
+            h->overflow_wave = true;
+            for (int k = 0; k < N_CLASSES; ++k) {
+                ClassState& cs = h->cls[k];
+                const int per = 32 >> h->cur_gs[k];
+                const int left = cs.n_members - cs.episode_grid * per;
+                if (!cs.n_members || left <= 0) continue;
+                cs.gs2 = h->cur_gs[k];
+                cs.grid2 = (left + per - 1) / per;
+            }
         }
         return;
     }
@@ -837,7 +882,7 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
             if (h->cls[k].n_batches && h->cls[k].episode_grid * per < h->cls[k].n_members) single_round = false;
         }
         bool second = false;
-        for (int k = 0; k < N_CLASSES; ++k) second |= h->cls[k].grid2 > 0;
+        for (int k = 0; k < N_CLASSES; ++k) second |= h->cls[k].grid2 > 0 && !h->overflow_wave;
         if (single_round || second) { park_ticks = 160; cap_frac = 0.25; }
     }
     if (h->opt.park_ticks >= 0) park_ticks = h->opt.park_ticks;
@@ -854,7 +899,19 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
     const bool warp_mode = h->n_creatures <= warp_mode_max;
     if (warp_mode) park_ticks = 0;
     const bool trace = h->opt.trace != 0;
-    for (int k = N_CLASSES - 1; k >= 0; --k) {
+    // Launch order = decreasing shared memory per CTA (first-fit decreasing): the work distributor places the CTAs of the
+    // launches in order, and a CTA that finds no SM with enough free shared memory holds back every launch behind it.
+    // Measured (profiles/r2_timeline_ea_gen2_before.txt): with the 33-44 body class at 8 lanes per creature (22 KB per CTA)
+    // launched first, its 822 CTAs left < 109 KB free on every SM, the 23-32 body class (109 KB per CTA) could not start, and
+    // all seven smaller classes waited behind it until the first launch had finished (1.3 s of a 3.8 s evaluation).
+    int launch_order[N_CLASSES];
+    for (int k = 0; k < N_CLASSES; ++k) launch_order[k] = k;
+    std::stable_sort(launch_order, launch_order + N_CLASSES, [&](int a, int b) {
+        const size_t sa = g_classes(a).hot_bytes(warp_mode ? 5 : class_gs(h, a)), sb = g_classes(b).hot_bytes(warp_mode ? 5 : class_gs(h, b));
+        return sa != sb ? sa > sb : a > b;
+    });
+    for (int oi = 0; oi < N_CLASSES; ++oi) {
+        const int k = launch_order[oi];
         ClassState& cs = h->cls[k];
         if (!cs.n_batches) continue;
         CK(cudaMemsetAsync(cs.d_queue, 0, sizeof(int), cs.stream));
@@ -894,14 +951,15 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
         cs.park = park;
         g_classes(k).episode(h->image, class_gs(h, k), cs.episode_grid, cs.stream, cs.d_state, cs.d_lane_creature, cs.n_members, cs.d_queue, h->dpop,
                              h->d_ter, h->d_consts, max_ticks, h->d_fitness, h->d_ticks, h->d_alive, h->d_status, h->d_counters,
-                             park, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive, cs.grid2 > 0 ? 0 : 1);
+                             park, cs.d_state2, cs.d_lc_work[0], cs.d_n_alive, (cs.grid2 > 0 && !h->overflow_wave) ? 0 : 1);
         CK(cudaMemcpyAsync(cs.h_n_alive, cs.d_n_alive, sizeof(int), cudaMemcpyDeviceToHost, cs.stream));
         CK(cudaEventRecord(cs.t_end, cs.stream));
         h->launches++;
     }
     // second launches (after ALL first launches, so that their CTAs queue behind them): the creatures a class could not seat
     // in its first round, in wide groups, on the columns behind the first launch's
-    for (int k = N_CLASSES - 1; k >= 0 && !warp_mode; --k) {
+    for (int oi = 0; oi < N_CLASSES && !warp_mode; ++oi) {
+        const int k = launch_order[oi];
         ClassState& cs = h->cls[k];
         if (!cs.n_batches || cs.grid2 <= 0) continue;
         const int per1 = 32 >> class_gs(h, k);
@@ -930,7 +988,8 @@ static int launch_episodes(rem2d_handle* h, int max_ticks) {
                 if (!h->tail_used[s] || cudaStreamQuery(h->tail_pool[s]) == cudaSuccess) { rr = s + 1; h->tail_used[s] = 1; return h->tail_pool[s]; }
             }
             cudaStream_t st = nullptr;
-            if (h->tail_pool.size() < 4096 && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess) {
+            // highest priority: tail CTAs are placed before the queued overflow-wave CTAs of the episode launches
+            if (h->tail_pool.size() < 4096 && cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, h->prio_high) == cudaSuccess) {
                 h->tail_pool.push_back(st); h->tail_used.push_back(1);
                 return st;
             }

@@ -25,6 +25,10 @@ if __name__ == "__main__":
         nb = np.diff(pop.body_off)
         hist = [int(((nb > (bounds[i - 1] if i else 0)) & (nb <= b)).sum()) for i, b in enumerate(bounds)]
         print("generation %d: %d creatures, mean bodies %.1f, class histogram %s" % (gen, pop.n_creatures, nb.mean(), hist), flush=True)
+        os.makedirs("/tmp/rem2d_cache", exist_ok=True)
+        np.savez("/tmp/rem2d_cache/ea_pop_gen%d.npz" % gen, **{k: getattr(pop, k) for k in (
+            "body_off", "shape", "hx", "hy", "x0", "y0", "a0", "node_index", "type_ref", "joint_parent", "anchor_a", "anchor_b", "lower",
+            "upper", "max_torque", "ctrl")})
         ref = None
         for c in sys.argv[2:] or [""]:
             g = Engine(device=0); g.set_terrain(ys, K.TERRAIN_STEP)

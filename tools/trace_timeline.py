@@ -7,8 +7,14 @@ from gym_rem2d_b200 import constants as K, terrain
 from gym_rem2d_b200.capi import Engine
 from gym_rem2d_b200.population import random_population
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-pop = random_population(n, ("lsystem",), seed=2, cache_dir="/tmp/rem2d_cache")
+if len(sys.argv) > 1 and sys.argv[1].endswith(".npz"):        # a population table saved by tools/ea_pop_sweep.py
+    from gym_rem2d_b200.flatten import PopulationTable
+    z = np.load(sys.argv[1])
+    pop = PopulationTable(*(z[k] for k in ("body_off", "shape", "hx", "hy", "x0", "y0", "a0", "node_index", "type_ref", "joint_parent",
+                                           "anchor_a", "anchor_b", "lower", "upper", "max_torque", "ctrl")))
+else:
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+    pop = random_population(n, ("lsystem",), seed=2, cache_dir="/tmp/rem2d_cache")
 xs, ys = terrain.generate_terrain()
 e = Engine(device=0)
 e.set_terrain(ys, K.TERRAIN_STEP)
@@ -32,7 +38,7 @@ for k in range(9):
     m = a[:, :, 0][valid].min()
     t0 = m if t0 is None else min(t0, m)
 out = {}
-BIN = 50
+BIN = max(50, int(e.last_step_ms() / 16 / 50) * 50)
 for k, a in traces.items():
     t = (a[:, :, 0].astype(np.int64) - int(t0)) / 1000.0       # ms
     live = (a[:, :, 1] & 0xff).astype(np.int64)
