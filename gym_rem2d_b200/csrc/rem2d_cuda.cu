@@ -157,7 +157,7 @@ struct ClassState {
 };
 
 // Tuning / diagnostic options (rem2d_set_option; the REM2D_* environment variables of the same names are read ONCE, at
-// rem2d_create, as initial values - tools/sweep_policy.py and the tests use them). Defaults are the measured optimum.
+// rem2d_create, as initial values - tools/sweep_groups.py, tools/ea_pop_sweep.py and the tests use them). Defaults are the measured optimum.
 struct Options {
     int warp_mode_max = -1;      // largest population that runs one warp per creature from tick 0 (-1: 48 per SM)
     int park_ticks = -1;         // park threshold of the queue mode (-1: automatic, 0: never park)
@@ -866,11 +866,11 @@ static int launch_phased(rem2d_handle* h, int max_ticks) {
 static int launch_episodes(rem2d_handle* h, int max_ticks) {
     if (!h->have_terrain) { h->err = "run_episodes: no terrain set"; return REM2D_E_INVALID; }
     // creatures still alive after park_ticks are finished by tail-mode launches (REM2D_PARK_TICKS=0 disables parking)
-    // Measured on B200 (tools/sweep_policy.py, 65536 L-system creatures): parking at 256 ticks (~0.5 % of the creatures) is
-    // the best trade: a tail warp finishes a creature 3-4x sooner than its bulk lane would, but it occupies a whole warp, so
+    // Measured on B200 (tools/sweep_groups.py, 65536 L-system creatures): parking at 200-256 ticks (~0.5-1.4 % of the creatures)
+    // is the best trade: a tail warp finishes a creature 3-4x sooner than its bulk lane would, but it occupies a whole warp, so
     // earlier thresholds (thousands of parked creatures) slow the bulk down more than they shorten the critical path; later
     // ones leave the longest-lived creatures on the slow path. Drain / late-start parking never paid off. The number of
-    // parked creatures per class is bounded (n/16, at most 4 per SM): in an evolved population where most creatures live
+    // parked creatures per class is bounded (a quarter of the class, at most 16 per SM): in an evolved population where most creatures live
     // long, the rest simply stay on their lanes.
     int park_ticks = 200;            // measured (tools/sweep_groups.py, 65536 creatures): 256 -> 820 ms, 200 -> 790 ms, 160 -> 930 ms
     double cap_frac = 0.25;
