@@ -116,9 +116,12 @@ __global__ void fp32_issue_kernel(float* out, int iters, float b, float c) {
 struct Buf { void* p = nullptr; size_t cap = 0; };
 static cudaError_t ensure(Buf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return cudaSuccess;
+    // a buffer that has to grow will grow again (an evolving population shifts towards the large classes generation by
+    // generation): 50 % headroom then, 12.5 % on the first allocation
+    const bool regrow = b.p != nullptr;
     if (b.p) cudaFree(b.p);
     b.p = nullptr; b.cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
+    size_t want = bytes + (regrow ? bytes / 2 : bytes / 8) + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e == cudaSuccess) b.cap = want;
     return e;
@@ -162,6 +165,7 @@ struct Options {
     int warp_mode_max = -1;      // largest population that runs one warp per creature from tick 0 (-1: 48 per SM)
     int park_ticks = -1;         // park threshold of the queue mode (-1: automatic, 0: never park)
     double park_cap = -1.0;      // fraction of a class that may be parked (-1: automatic)
+    int priority_mode = 1;       // rem2d_set_priority: 0 = expected lifetime >= 130 ticks first, 1 = and among those the longest first
     int overflow_wave = 1;       // queue the CTAs a class could not seat in its first wave behind the first launches (see choose_groups_and_grids)
     int image = -1;              // kernel image of the episode launches (-1: automatic, 0: ~200 registers, 1: 128 registers)
     int park_late_ticks = -1;    // park threshold of creatures pulled after the first round (-1: same as park_ticks)
@@ -268,13 +272,14 @@ static bool set_option(Options& o, const char* name, double v) {
     else if (n == "phased") o.phased = (int)v;
     else if (n == "image") o.image = std::max(-1, std::min(1, (int)v));
     else if (n == "overflow_wave") o.overflow_wave = (int)v != 0;
+    else if (n == "priority_mode") o.priority_mode = (int)v;
     else if (n.rfind("class_gs_", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] < '0' + N_CLASSES) o.class_gs[n[9] - '0'] = (int)v;
     else return false;
     return true;
 }
 static void options_from_env(Options& o) {
     static const char* names[] = {"warp_mode_max", "park_ticks", "park_cap", "park_late_ticks", "park_lead", "smem_budget_kb", "small_weight", "min_class",
-                                  "group_shift", "tail_group_shift", "second_group_shift", "trace", "image", "overflow_wave", "wide_weight"};
+                                  "group_shift", "tail_group_shift", "second_group_shift", "trace", "image", "overflow_wave", "wide_weight", "priority_mode"};
     for (const char* n : names) {
         std::string env = "REM2D_";
         for (const char* q = n; *q; ++q) env += (char)toupper(*q);
@@ -651,10 +656,18 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         auto& m = members[k];
         if (m.empty()) continue;
         // big creatures first: batches of similar size limit lane divergence, and the costly batches start early; creatures
-        // the caller expects to be long-lived (rem2d_set_priority) go to the very front of the class queue
+        // the caller expects to be long-lived (rem2d_set_priority: >= 130 ticks, i.e. they outrun the wall of death) go to
+        // the very front of the class queue, the longest-lived first in buckets of 32 ticks (longest-processing-time-first).
+        // Measured with the parents' lifetimes as the hint (profiles/r2_ea_pop_sweep.txt): selected populations, where most
+        // creatures are long-lived, evaluate 7-11 % faster with the ordering than with the threshold alone (1570 -> 1480,
+        // 2575 -> 2380, 2130 -> 1900 ms); a random population with a perfect hint gains 20 % either way (800 -> 640 ms).
         const bool prio = (int)h->priority.size() == n;
         std::stable_sort(m.begin(), m.end(), [&](int a, int b) {
-            const int la = prio && h->priority[a] >= 130.0f, lb = prio && h->priority[b] >= 130.0f;
+            int la = prio && h->priority[a] >= 130.0f, lb = prio && h->priority[b] >= 130.0f;
+            if (prio && h->opt.priority_mode == 1) {      // ... and among those the longest expected lifetime first, in buckets of 32 ticks
+                la = h->priority[a] >= 128.0f ? (int)std::min(h->priority[a], 4096.0f) >> 5 : 0;
+                lb = h->priority[b] >= 128.0f ? (int)std::min(h->priority[b], 4096.0f) >> 5 : 0;
+            }
             if (la != lb) return la > lb;
             return (pop->body_off[a + 1] - pop->body_off[a]) > (pop->body_off[b + 1] - pop->body_off[b]);
         });

@@ -21,6 +21,7 @@ if __name__ == "__main__":
     xs, ys = terrain.generate_terrain()
     bounds = [1, 2, 4, 8, 12, 16, 22, 32, 44]
     rng = np.random.RandomState(0)
+    parent_ticks = None
     for gen in range(3):
         nb = np.diff(pop.body_off)
         hist = [int(((nb > (bounds[i - 1] if i else 0)) & (nb <= b)).sum()) for i, b in enumerate(bounds)]
@@ -32,10 +33,12 @@ if __name__ == "__main__":
         ref = None
         for c in sys.argv[2:] or [""]:
             g = Engine(device=0); g.set_terrain(ys, K.TERRAIN_STEP)
-            for kv in [kv for kv in c.split(";") if kv]:
+            for kv in [kv for kv in c.split(";") if kv and kv != "PRIO"]:
                 k_, v_ = kv.split("="); g.set_option(k_, float(v_))
             ms = []
             for _ in range(2):
+                if "PRIO" in c.split(";") and parent_ticks is not None:
+                    g.set_priority(parent_ticks)            # lifetimes of the (unmutated) parents: what ea.run2D passes
                 f, t = g.evaluate(pop, K.EVALUATION_STEPS)
                 ms.append(g.last_step_ms())
             if ref is None:
@@ -47,3 +50,4 @@ if __name__ == "__main__":
         asp = rng.randint(0, len(fit), size=(len(fit), 4))
         win = asp[np.arange(len(fit)), np.argmax(fit[asp], axis=1)]
         pop = pop.select(win)
+        parent_ticks = ticks[win].astype(np.float32)
