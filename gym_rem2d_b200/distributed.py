@@ -50,7 +50,7 @@ def gather_fitness(local_fitness, local_idx, n_total, device=None):
     return out
 
 
-def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=None, gather_ticks=False):
+def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=None, gather_ticks=False, expected_ticks=None):
     """Evaluate this rank's shard of ``table`` on ``engine`` and gather everyone's fitness: the multi-GPU form of
     ``pool.map(evaluate, population, chunksize=ceil(pop/n))`` (REM2D_main.py:256-262). ``engine`` is a long-lived
     ``capi.Engine`` (its device buffers are grow-only and reused from generation to generation); a zero-argument factory is
@@ -63,6 +63,8 @@ def evaluate_sharded(table, engine, max_ticks, rank=None, world=None, device=Non
         world = dist.get_world_size() if dist.is_initialized() else 1
     sub, idx = shard_population(table, rank, world)
     eng = engine() if callable(engine) else engine
+    if expected_ticks is not None:          # scheduling hint (expected lifetimes of the WHOLE population): this shard's part
+        eng.set_priority(np.asarray(expected_ticks, np.float32)[idx])
     fit, ticks = eng.evaluate(sub, max_ticks)
     if gather_ticks:                       # lifetimes <= max_ticks are exact in float32
         return (gather_fitness(fit, idx, table.n_creatures, device=device),
@@ -114,14 +116,23 @@ _DTYPES = (np.int32, np.uint8, np.float32, np.float32, np.float32, np.float32, n
            np.float32, np.float32, np.float32, np.float32, np.float64)
 
 
-def evaluate_broadcast(table, engine, max_ticks, device=None, gather_ticks=False):
-    """Collective: rank 0 passes the generation's table (None = stop), the others pass None; everybody returns the fitness of
-    the whole population (or None on stop) and what evaluate_sharded returns second."""
+def evaluate_broadcast(table, engine, max_ticks, device=None, gather_ticks=False, expected_ticks=None):
+    """Collective: rank 0 passes the generation's table (None = stop) and, optionally, the expected lifetimes of its creatures
+    (the scheduling hint of rem2d_set_priority; broadcast with the table, zeros = no hint); the others pass None; everybody
+    returns the fitness of the whole population (or None on stop) and what evaluate_sharded returns second."""
+    import torch
     import torch.distributed as dist
     table = broadcast_table(table, 0, device)
     if table is None:
         return None, 0
-    return evaluate_sharded(table, engine, max_ticks, dist.get_rank(), dist.get_world_size(), device, gather_ticks)
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    hint = torch.zeros(table.n_creatures, dtype=torch.float32, device=dev)
+    if dist.get_rank() == 0 and expected_ticks is not None and len(expected_ticks) == table.n_creatures:
+        hint.copy_(torch.as_tensor(np.asarray(expected_ticks, np.float32)))
+    dist.broadcast(hint, 0)
+    hint = hint.cpu().numpy()
+    return evaluate_sharded(table, engine, max_ticks, dist.get_rank(), dist.get_world_size(), device, gather_ticks,
+                            hint if hint.any() else None)
 
 
 def serve_evaluations(engine, max_ticks, device=None, gather_ticks=False):

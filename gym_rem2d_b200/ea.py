@@ -213,7 +213,8 @@ class run2D:
         if self.distributed:
             # rank 0 drives the loop and broadcasts the generation's table; the other ranks sit in distributed.serve_evaluations
             from . import distributed as rdist
-            fit, lifetimes = rdist.evaluate_broadcast(table, env.engine, self.EVALUATION_STEPS, gather_ticks=True)
+            hint = self.expected_ticks if self.expected_ticks is not None and len(self.expected_ticks) == table.n_creatures else None
+            fit, lifetimes = rdist.evaluate_broadcast(table, env.engine, self.EVALUATION_STEPS, gather_ticks=True, expected_ticks=hint)
             self.last_lifetimes = lifetimes
             return [float(f) for f in fit], int(lifetimes.sum())
         if self.expected_ticks is not None and len(self.expected_ticks) == table.n_creatures and hasattr(env, "engine"):

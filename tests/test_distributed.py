@@ -83,7 +83,8 @@ def _serve_worker(rank, world, port, table, ys, ret):
         out = []
         for gen in range(2):
             sub = table if gen == 0 else table.select(np.arange(table.n_creatures)[::-1].copy())
-            fit, lifetimes = rdist.evaluate_broadcast(sub, e, 300, gather_ticks=True)
+            hint = np.arange(sub.n_creatures, dtype=np.float32) * 20 if gen == 1 else None      # scheduling hint: results unchanged
+            fit, lifetimes = rdist.evaluate_broadcast(sub, e, 300, gather_ticks=True, expected_ticks=hint)
             out.append((fit, lifetimes))
         assert rdist.broadcast_table(None, 0) is None          # stop signal
         ret[0] = out
