@@ -278,6 +278,35 @@ def test_config4_4096_cppn_ce_rough():
     assert g.counters() == co
 
 
+def test_ea_configured_population_mixed_widths_and_overflow_wave():
+    """A population as run_deap configures it (max_size 40: creatures of up to 41 bodies) that does not fit on the GPU at once:
+    the 33-44 body class runs 8 lanes per creature next to one-lane classes, the first wave is sized to 75 % of the shared
+    memory, every class queues an overflow wave behind the first launches, and the lifetime hint reorders the class queues.
+    2048 distinct creatures (checked against the oracle), tiled 24 times."""
+    from gym_rem2d_b200 import ea
+    from gym_rem2d_b200.modules import get_module_list
+    random.seed(21); np.random.seed(21)
+    cfg = ea.default_config(enc="lsystem")
+    base = flatten_population([Individual.random(get_module_list(), cfg) for _ in range(2048)], 7)
+    nb = np.diff(base.body_off)
+    assert (nb > 32).sum() > 100 and nb.max() <= 44
+    xs, ys = terrain.generate_terrain()
+    fo, to, co = _oracle_eval(base, ys)
+    pop = base.select(np.tile(np.arange(2048), 24))
+    g = Engine(device=0)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    fg, tg = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg, np.tile(to, 24)) and np.array_equal(fg, np.tile(fo, 24))
+    assert g.launch_count() > 2 * 9                         # first launches + overflow waves (+ tails)
+    g.set_priority(np.tile(to, 24).astype(np.float32))      # longest-lived first: another order, the same results
+    fg2, tg2 = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg2, tg) and np.array_equal(fg2, fg)
+    g.set_option("overflow_wave", 0)
+    fg3, tg3 = g.evaluate(pop, K.EVALUATION_STEPS)
+    assert np.array_equal(tg3, tg) and np.array_equal(fg3, fg)
+    g.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Lanes per creature (group shift): the same kernels with G = 1, 2, 4, 8, 32 lanes per creature must all equal the oracle.
 @pytest.mark.parametrize("gs", ["0", "1", "2", "3", "5"])
