@@ -662,11 +662,14 @@ static int upload_impl(rem2d_handle* h, const rem2d_population* pop, bool do_res
         // creatures are long-lived, evaluate 7-11 % faster with the ordering than with the threshold alone (1570 -> 1480,
         // 2575 -> 2380, 2130 -> 1900 ms); a random population with a perfect hint gains 20 % either way (800 -> 640 ms).
         const bool prio = (int)h->priority.size() == n;
+        // "long-lived" = expected to be alive when the wall of death has passed the start pad (root at x = 5: tick 125 at the
+        // reference's 0.04 per tick, + 4 %)
+        const float long_lived = (h->cfg.terminate && h->cfg.wod_speed > 0.0) ? (float)(5.2 / h->cfg.wod_speed) : 130.0f;
         std::stable_sort(m.begin(), m.end(), [&](int a, int b) {
-            int la = prio && h->priority[a] >= 130.0f, lb = prio && h->priority[b] >= 130.0f;
+            int la = prio && h->priority[a] >= long_lived, lb = prio && h->priority[b] >= long_lived;
             if (prio && h->opt.priority_mode == 1) {      // ... and among those the longest expected lifetime first, in buckets of 32 ticks
-                la = h->priority[a] >= 128.0f ? (int)std::min(h->priority[a], 4096.0f) >> 5 : 0;
-                lb = h->priority[b] >= 128.0f ? (int)std::min(h->priority[b], 4096.0f) >> 5 : 0;
+                la = la ? 1 + ((int)std::min(h->priority[a], 8192.0f) >> 5) : 0;
+                lb = lb ? 1 + ((int)std::min(h->priority[b], 8192.0f) >> 5) : 0;
             }
             if (la != lb) return la > lb;
             return (pop->body_off[a + 1] - pop->body_off[a]) > (pop->body_off[b + 1] - pop->body_off[b]);
