@@ -174,6 +174,10 @@ class run2D:
         # counters and launches the tail kernels) is starved by the busy workers and the chunked evaluations take 6-8 s per
         # generation instead of 1 s for one evaluation of the whole table (profiles/r2_ea_config5.json)
         self.pipeline_creatures = 0
+        # packed populations: evaluate the first half of a generation while the workers expand the second half. Measured at
+        # population 65536 (1 GPU, 14 workers): 4.33 s per generation against 4.93 s - two evaluations of 32768 cost 0.3-0.5 s
+        # more than one of 65536, the overlap hides 0.8-1.1 s of expansion (REM2D_EA_PIPELINE=0 turns it off)
+        self.pipeline_halves = os.environ.get("REM2D_EA_PIPELINE", "1") != "0"
         self.materialize_result = True       # run_deap returns Individuals (False: PackedIndividuals where the population was packed)
         # persistent workers, started BEFORE any CUDA work of this process (the engine is created lazily, later)
         # (forkserver re-imports __main__ in the workers, which an interactive / stdin main cannot offer: plain fork there - still
@@ -244,6 +248,32 @@ class run2D:
         which dominates a generation at large population sizes. Returns (offspring, fitness list, timing)."""
         t0 = time.perf_counter()
         packed = bool(parents) and isinstance(parents[0], PackedIndividual)
+        if packed and self.pool is not None and self.pipeline_halves and not self.distributed:
+            # two halves: the first half of the chunks is evaluated while the workers expand the second half
+            jobs = self._packed_jobs(parents)
+            it = self.pool.imap(_vary_chunk_packed, jobs)
+            half = max(1, len(jobs) // 2)
+            expected, offspring, fit, lifetimes, tables, steps, eval_s, dev_s = self.expected_ticks, [], [], [], [], 0, 0.0, 0.0
+            for lo, hi in ((0, half), (half, len(jobs))):
+                parts = [next(it) for _ in range(lo, hi)]
+                if not parts:
+                    continue
+                table = concat([t for _, t in parts])
+                n0 = len(offspring)
+                offspring.extend(PackedIndividual(b) for bl, _ in parts for b in bl)
+                if expected is not None and len(expected) == len(parents):
+                    self.expected_ticks = expected[n0:n0 + table.n_creatures]
+                te = time.perf_counter()
+                f, s_ = self.evaluate_table(table)
+                eval_s += time.perf_counter() - te
+                dev_s += self.last_device_s
+                fit.extend(f); steps += s_; lifetimes.append(self.last_lifetimes); tables.append(table)
+            self.expected_ticks = expected
+            self.last_lifetimes = np.concatenate(lifetimes)
+            total = time.perf_counter() - t0
+            return offspring, fit, {"expand_s": total - eval_s, "evaluate_s": eval_s, "evaluate_hidden_s": 0.0, "creature_steps": steps,
+                                    "evaluate_device_s": dev_s,
+                                    "mean_bodies": float(np.concatenate([np.diff(t.body_off) for t in tables]).mean())}
         if self.pool is None or len(parents) < 4 * self.workers or self.distributed or self.pipeline_creatures <= 0 or packed:
             offspring, table = self.vary_and_expand(parents)
             t1 = time.perf_counter()
@@ -268,21 +298,25 @@ class run2D:
         total = time.perf_counter() - t0
         return offspring, fit, {"expand_s": total - eval_s, "evaluate_s": eval_s, "evaluate_hidden_s": eval_s, "creature_steps": steps}
 
+    def _packed_jobs(self, parents):
+        """Worker jobs for packed parents: every distinct parent of a chunk once as bytes + the chunk as indices into them."""
+        jobs = []
+        for chunk in self._chunks(parents):
+            slot, blobs, idx = {}, [], []
+            for p in chunk:
+                k = slot.get(id(p))
+                if k is None:
+                    k = slot[id(p)] = len(blobs)
+                    blobs.append(p.blob)
+                idx.append(k)
+            jobs.append((blobs, idx, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA,
+                         random.getrandbits(48)))
+        return jobs
+
     def vary_and_expand(self, parents):
         """clone + mutate + expand: in the workers when there is a pool, else here."""
         if self.pool is not None and parents and isinstance(parents[0], PackedIndividual):
-            jobs = []
-            for chunk in self._chunks(parents):
-                slot, blobs, idx = {}, [], []
-                for p in chunk:
-                    k = slot.get(id(p))
-                    if k is None:
-                        k = slot[id(p)] = len(blobs)
-                        blobs.append(p.blob)
-                    idx.append(k)
-                jobs.append((blobs, idx, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA,
-                             random.getrandbits(48)))
-            parts = self.pool.map(_vary_chunk_packed, jobs)
+            parts = self.pool.map(_vary_chunk_packed, self._packed_jobs(parents))
             return [PackedIndividual(b) for bl, _ in parts for b in bl], concat([t for _, t in parts])
         if self.pool is not None and len(parents) >= 4 * self.workers:
             jobs = [(c, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, random.getrandbits(48))

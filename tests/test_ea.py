@@ -91,6 +91,7 @@ def test_packed_population_generations(tmp_path):
     cfg["ea"]["batch_size"] = "160"
     cfg["experiment"]["checkpoint_frequency"] = "2"
     run = ea.run2D(cfg, str(tmp_path), env=StubEnv(), workers=2)
+    run.pipeline_halves = False                        # one evaluation per generation (the pipelined form has its own test)
     try:
         pop = run.run_deap(cfg, n_generations=3)
         assert len(pop) == 160 and all(isinstance(p, Individual) for p in pop)
@@ -114,6 +115,26 @@ def test_packed_population_generations(tmp_path):
         pop2 = run2.run(cfg, continue_progression=True, n_generations=1)
         assert len(pop2) == 160 and isinstance(pop2[0], ea.PackedIndividual) and isinstance(pop2[0].unpack(), Individual)
         run2.close()
+    finally:
+        run.close()
+
+
+def test_packed_population_two_halves_pipeline(monkeypatch):
+    """Default for packed populations (REM2D_EA_PIPELINE=0 turns it off): the first half of a generation is evaluated while the
+    workers expand the second half; fitness and lifetimes still land on the right individuals."""
+    monkeypatch.delenv("REM2D_EA_PIPELINE", raising=False)
+    random.seed(6)
+    cfg = ea.default_config(enc="lsystem", mr=0.3, mmr=0.3, ms=0.3)
+    cfg["ea"]["batch_size"] = "160"
+    run = ea.run2D(cfg, "", env=StubEnv(), workers=2)
+    try:
+        assert run.pipeline_halves
+        pop = run.run_deap(cfg, n_generations=3)
+        from gym_rem2d_b200.flatten import flatten_population
+        nb = np.diff(flatten_population(pop, run.TREE_DEPTH).body_off)
+        assert len(pop) == 160 and [p.fitness for p in pop] == [float(n) for n in nb]
+        assert [p.lifetime for p in pop] == [int(n) * 10 for n in nb]
+        assert all(g["creature_steps"] == int(nb_.sum()) * 10 for g, nb_ in [(run.generation_log[-1], nb)])
     finally:
         run.close()
 
