@@ -185,11 +185,15 @@ class PopulationTable:
         nb = (self.body_off[1:] - self.body_off[:-1])[idx]
         boff = np.zeros(len(idx) + 1, dtype=np.int32)
         np.cumsum(nb, out=boff[1:])
-        bsel = np.concatenate([np.arange(self.body_off[i], self.body_off[i + 1]) for i in idx]) if len(idx) else np.zeros(0, np.int64)
-        joff = self.joint_off()
-        jsel = np.concatenate([np.arange(joff[i], joff[i + 1]) for i in idx]) if len(idx) else np.zeros(0, np.int64)
-        bsel = bsel.astype(np.int64)
-        jsel = jsel.astype(np.int64)
+
+        def ranges(start, count):          # concatenation of arange(start[k], start[k] + count[k]) without a Python loop
+            count = count.astype(np.int64)
+            first = np.zeros(len(count) + 1, np.int64)
+            np.cumsum(count, out=first[1:])
+            return np.repeat(start.astype(np.int64) - first[:-1], count) + np.arange(first[-1], dtype=np.int64)
+
+        bsel = ranges(self.body_off[:-1][idx], nb)
+        jsel = ranges(self.joint_off()[:-1][idx], nb - 1)
         return PopulationTable(boff, self.shape[bsel], self.hx[bsel], self.hy[bsel], self.x0[bsel], self.y0[bsel],
                                self.a0[bsel], self.node_index[bsel], self.type_ref[bsel], self.joint_parent[jsel],
                                self.anchor_a[jsel], self.anchor_b[jsel], self.lower[jsel], self.upper[jsel],
