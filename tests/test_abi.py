@@ -63,3 +63,25 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "librem2d_oracle" not in text, f
+
+
+def test_documented_options_are_the_implemented_ones():
+    """DESIGN.md's option list, the names rem2d_set_option of the CUDA library parses (read from its source) and the names the
+    oracle's stub accepts are the same set; unknown names are an error."""
+    import ctypes
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "DESIGN.md")).read()
+    block = doc[doc.index("Options (`rem2d_set_option`"):]
+    block = block[:block.index("Defaults are")]
+    documented = set(re.findall(r"`([a-z_0-9<>]+)`", block)) - {"rem2d_set_option"}
+    src = open(os.path.join(root, "gym_rem2d_b200", "csrc", "rem2d_cuda.cu")).read()
+    body = src[src.index("static bool set_option("):src.index("static void options_from_env(")]
+    implemented = set(re.findall(r'n == "([a-z_0-9]+)"', body)) | {"class_gs_<k>"}
+    assert documented == implemented, (documented ^ implemented)
+    from oracle.oracle import OracleEngine
+    e = OracleEngine()
+    for name in sorted(implemented):
+        e.set_option(name.replace("<k>", "3"), 1.0)
+    with pytest.raises(Exception):
+        e.set_option("no_such_option", 1.0)
