@@ -278,6 +278,26 @@ def test_config4_4096_cppn_ce_rough():
     assert g.counters() == co
 
 
+def test_full_size_population_is_order_independent():
+    """BASELINE's full size (65536 L-system creatures, the bench population) through a size-independent property: a creature's
+    fitness and lifetime do not depend on its position in the population - a permuted population lands on other lanes, other
+    rounds of the class queues and other tail launches, and must give the permuted results; 4096 of them are also checked
+    against the oracle."""
+    from gym_rem2d_b200.population import random_population
+    pop = random_population(65536, ("lsystem",), seed=2, workers=8)
+    xs, ys = terrain.generate_terrain()
+    g = Engine(device=0)
+    g.set_terrain(ys, K.TERRAIN_STEP)
+    f, t = g.evaluate(pop, K.EVALUATION_STEPS)
+    perm = np.random.RandomState(5).permutation(65536)
+    f2, t2 = g.evaluate(pop.select(perm), K.EVALUATION_STEPS)
+    assert np.array_equal(t2, t[perm]) and np.array_equal(f2, f[perm])
+    sample = np.sort(perm[:4096])
+    fo, to, _ = _oracle_eval(pop.select(sample), ys)
+    assert np.array_equal(t[sample], to) and np.array_equal(f[sample], fo)
+    g.close()
+
+
 def test_ea_configured_population_mixed_widths_and_overflow_wave():
     """A population as run_deap configures it (max_size 40: creatures of up to 41 bodies) that does not fit on the GPU at once:
     the 33-44 body class runs 8 lanes per creature next to one-lane classes, the first wave is sized to 75 % of the shared

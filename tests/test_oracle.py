@@ -334,3 +334,23 @@ def test_disc_rolls_without_slipping_until_the_slope_exceeds_three_mu(tan_slope)
         assert abs(accel - 10.0 * math.sin(th) * 2.0 / 3.0) < 0.01 * accel and abs(slip_ratio - 1.0) < 0.01
     else:
         assert abs(accel - 10.0 * (math.sin(th) - 0.5 * math.cos(th))) < 0.02 * accel and slip_ratio > 1.2
+
+
+def test_results_do_not_depend_on_population_order_or_company():
+    """Size-independent property of the path: every creature is its own world, so its fitness and lifetime depend neither on
+    its position in the population nor on which other creatures are evaluated with it (what makes sharding by individual
+    and the tiled populations of the GPU tests legitimate)."""
+    random.seed(17)
+    pop = flatten_population([Individual.random(encoding="lsystem") for _ in range(48)])
+    xs, ys = terrain.generate_terrain()
+    e = OracleEngine(threads=4)
+    e.set_terrain(ys, K.TERRAIN_STEP)
+    f, t = e.evaluate(pop, 400)
+    perm = np.random.RandomState(3).permutation(48)
+    f2, t2 = e.evaluate(pop.select(perm), 400)
+    assert np.array_equal(f2, f[perm]) and np.array_equal(t2, t[perm])
+    sub = np.array([5, 5, 40, 0, 17])
+    f3, t3 = e.evaluate(pop.select(sub), 400)
+    assert np.array_equal(f3, f[sub]) and np.array_equal(t3, t[sub])
+    f4, t4 = e.evaluate(pop, 400)                     # and an evaluation leaves nothing behind in the engine
+    assert np.array_equal(f4, f) and np.array_equal(t4, t)
