@@ -142,8 +142,9 @@ def ea_bench(args, rank, local_rank, world, cores):
                       "unit": "creature-steps/s", "n_gpus": world, "population": args.pop, "generations": len(gens), "host_workers": max(2, cores - 2),
                       "seconds_per_generation": secs / max(1, len(gens)),
                       "per_generation": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in g.items()} for g in gens],
-                      "note": "expand_s = selection + clone + mutate + genome.create + flatten in the worker pool (host Python); evaluate_s = "
-                              "GPU evaluation; with pipelining evaluate_s is hidden inside the expansion (evaluate_hidden_s)",
+                      "note": "expand_s = the part of selection + clone + mutate + genome.create + flatten (worker pool, host Python) that is "
+                              "not hidden behind an evaluation; evaluate_s = GPU evaluation incl. upload and read-back (one per generation, or "
+                              "two halves with the second half expanding meanwhile: single device, REM2D_EA_PIPELINE != 0)",
                       "initial_population_s": round(total - secs, 2)}))
     run.close()
     if world > 1:

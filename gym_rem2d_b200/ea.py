@@ -169,11 +169,6 @@ class run2D:
         self.expected_ticks = None           # scheduling hint for the next evaluation (parents' lifetimes)
         self.last_lifetimes = None
         self.last_device_s = 0.0
-        # evaluate as soon as this many expanded creatures have arrived (0: expand everything, then evaluate once). Off by
-        # default: measured at population 65536 with 14 workers on a 16-core box, the evaluation's host thread (it polls the park
-        # counters and launches the tail kernels) is starved by the busy workers and the chunked evaluations take 6-8 s per
-        # generation instead of 1 s for one evaluation of the whole table (profiles/r2_ea_config5.json)
-        self.pipeline_creatures = 0
         # packed populations: evaluate the first half of a generation while the workers expand the second half. Measured at
         # population 65536 (1 GPU, 14 workers): 4.33 s per generation against 4.93 s - two evaluations of 32768 cost 0.3-0.5 s
         # more than one of 65536, the overlap hides 0.8-1.1 s of expansion (REM2D_EA_PIPELINE=0 turns it off)
@@ -242,10 +237,12 @@ class run2D:
         return fit
 
     def vary_expand_evaluate(self, parents):
-        """One generation's variation, expansion and evaluation, PIPELINED when there is a worker pool and a single device:
-        the workers return (offspring, table) chunk by chunk in order, and as soon as ``pipeline_creatures`` creatures have
-        arrived they are evaluated on the GPU while the workers continue - evaluation hides behind the host-side expansion,
-        which dominates a generation at large population sizes. Returns (offspring, fitness list, timing)."""
+        """One generation's variation, expansion and evaluation. Packed populations on a single device are PIPELINED in two
+        halves: the workers return (offspring pickles, table) chunk by chunk in order, the first half of the chunks is evaluated
+        on the GPU while the workers expand the second half. (A finer-grained form - evaluate every few thousand creatures as
+        they arrive - was measured and dropped: many small evaluations each pay the lifetime of their longest-lived creature,
+        6-8 s per generation instead of 1 s for one evaluation, profiles/r2_ea_config5.json.) Returns (offspring, fitness
+        list, timing)."""
         t0 = time.perf_counter()
         packed = bool(parents) and isinstance(parents[0], PackedIndividual)
         # (single device only: on 2 GPUs the two half-size collective evaluations cost what the overlap hides - 3.45 vs 3.47 s)
@@ -272,32 +269,15 @@ class run2D:
             self.expected_ticks = expected
             self.last_lifetimes = np.concatenate(lifetimes)
             total = time.perf_counter() - t0
-            return offspring, fit, {"expand_s": total - eval_s, "evaluate_s": eval_s, "evaluate_hidden_s": 0.0, "creature_steps": steps,
+            return offspring, fit, {"expand_s": total - eval_s, "evaluate_s": eval_s, "creature_steps": steps,
                                     "evaluate_device_s": dev_s,
                                     "mean_bodies": float(np.concatenate([np.diff(t.body_off) for t in tables]).mean())}
-        if self.pool is None or len(parents) < 4 * self.workers or self.distributed or self.pipeline_creatures <= 0 or packed:
-            offspring, table = self.vary_and_expand(parents)
-            t1 = time.perf_counter()
-            fit, steps = self.evaluate_table(table)
-            t2 = time.perf_counter()
-            return offspring, fit, {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "evaluate_hidden_s": 0.0, "creature_steps": steps,
-                                    "evaluate_device_s": self.last_device_s, "mean_bodies": float(np.diff(table.body_off).mean())}
-        jobs = [(c, self.TREE_DEPTH, self.MORPH_MUTATION_RATE, self.MUTATION_RATE, self.MUT_SIGMA, random.getrandbits(48))
-                for c in self._chunks(parents)]
-        offspring, fit, pending, n_pending, steps, eval_s = [], [], [], 0, 0, 0.0
-        it = self.pool.imap(_vary_chunk, jobs)
-        for j in range(len(jobs)):
-            off, table = next(it)
-            offspring.extend(off)
-            pending.append(table); n_pending += table.n_creatures
-            if n_pending >= self.pipeline_creatures or j == len(jobs) - 1:
-                te = time.perf_counter()
-                f, s_ = self.evaluate_table(concat(pending) if len(pending) > 1 else pending[0])
-                eval_s += time.perf_counter() - te
-                fit.extend(f); steps += s_
-                pending, n_pending = [], 0
-        total = time.perf_counter() - t0
-        return offspring, fit, {"expand_s": total - eval_s, "evaluate_s": eval_s, "evaluate_hidden_s": eval_s, "creature_steps": steps}
+        offspring, table = self.vary_and_expand(parents)
+        t1 = time.perf_counter()
+        fit, steps = self.evaluate_table(table)
+        t2 = time.perf_counter()
+        return offspring, fit, {"expand_s": t1 - t0, "evaluate_s": t2 - t1, "creature_steps": steps,
+                                "evaluate_device_s": self.last_device_s, "mean_bodies": float(np.diff(table.body_off).mean())}
 
     def _packed_jobs(self, parents):
         """Worker jobs for packed parents: every distinct parent of a chunk once as bytes + the chunk as indices into them."""
