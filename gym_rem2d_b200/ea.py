@@ -12,9 +12,11 @@ reference's (Experiments/configuration_maker.py:10-63, 0.cfg).
 Host-side expansion (mutate -> genome.create -> flatten) is Python and dominates a generation at large population
 sizes, so variation AND expansion run in a PERSISTENT process pool (created in ``__init__``, i.e. before
 the CUDA context exists in this process; ``forkserver`` start method, so no worker ever inherits driver state): the parent
-only draws the tournament winners and ships chunks of parents, the workers deep-copy, mutate and flatten them and return
-(offspring, table). Evaluation itself is one ``rem2d_evaluate`` call per generation, or - under ``torch.distributed`` -
-one call per rank on its shard of the table plus one all_gather of the fitness vector (distributed.evaluate_sharded).
+only draws the tournament winners and ships chunks of parents, the workers clone, mutate and flatten them and return
+(offspring, table). Large populations live in the driving process as pickles (PackedIndividual), so that no individual is
+ever (un)pickled there. Evaluation is one ``rem2d_evaluate`` call per generation (two halves on a single device, the
+second half expanding while the first is evaluated), or - under ``torch.distributed`` - one call per rank on its shard of
+the table plus all_gathers of the fitness and lifetime vectors (distributed.evaluate_broadcast).
 Checkpoints are written under the reference's class paths (refpickle.py) and numbered by ABSOLUTE generation, so a resumed
 run never overwrites or re-reads an older population.
 """
