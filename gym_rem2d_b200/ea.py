@@ -175,6 +175,7 @@ class run2D:
         # population 65536 (1 GPU, 14 workers): 4.33 s per generation against 4.93 s - two evaluations of 32768 cost 0.3-0.5 s
         # more than one of 65536, the overlap hides 0.8-1.1 s of expansion (REM2D_EA_PIPELINE=0 turns it off)
         self.pipeline_halves = os.environ.get("REM2D_EA_PIPELINE", "1") != "0"
+        self.pipeline_min = 65536            # smallest population that is evaluated in two halves (measured at 65536 only)
         self.materialize_result = True       # run_deap returns Individuals (False: PackedIndividuals where the population was packed)
         # persistent workers, started BEFORE any CUDA work of this process (the engine is created lazily, later)
         # (forkserver re-imports __main__ in the workers, which an interactive / stdin main cannot offer: plain fork there - still
@@ -248,7 +249,9 @@ class run2D:
         t0 = time.perf_counter()
         packed = bool(parents) and isinstance(parents[0], PackedIndividual)
         # (single device only: on 2 GPUs the two half-size collective evaluations cost what the overlap hides - 3.45 vs 3.47 s)
-        if packed and self.pool is not None and self.pipeline_halves and not self.distributed:
+        # and only for populations whose halves still fill the GPU: a latency-bound evaluation takes one creature lifetime
+        # whatever its size (8192 creatures: 0.57 s for two halves against 0.24 s for one evaluation)
+        if packed and self.pool is not None and self.pipeline_halves and not self.distributed and len(parents) >= self.pipeline_min:
             # two halves: the first half of the chunks is evaluated while the workers expand the second half
             jobs = self._packed_jobs(parents)
             it = self.pool.imap(_vary_chunk_packed, jobs)

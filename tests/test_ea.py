@@ -127,6 +127,7 @@ def test_packed_population_two_halves_pipeline(monkeypatch):
     cfg = ea.default_config(enc="lsystem", mr=0.3, mmr=0.3, ms=0.3)
     cfg["ea"]["batch_size"] = "160"
     run = ea.run2D(cfg, "", env=StubEnv(), workers=2)
+    run.pipeline_min = 0                               # (by default only populations of >= 65536 are split)
     try:
         assert run.pipeline_halves
         pop = run.run_deap(cfg, n_generations=3)
